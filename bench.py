@@ -1,0 +1,301 @@
+#!/usr/bin/env python3
+"""bench.py -- pairings/sec of the batched BLS12-381 pairing path on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps K --warmup W                       # our arm
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                                # CPU arm (C oracle port)
+
+A "step" is one pass of the hot path (Miller loop + final exponentiation) over one batch of
+2^LOG2 synthetic (G1,G2) pairs per GPU (weak scaling).  `value` times the kernel with inputs
+already resident in HBM; `e2e` goes through the host-buffer C-ABI call (zkp_pairing_batch) from
+pinned host memory, copies included.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pairings_per_sec"
+UNIT = "pairings/s"
+# Algorithmic work (BASELINE.md section 2 / SURVEY 8d): 16,017 Fp-muls x 300 wide MACs per pairing
+FP_MULS_PER_PAIRING = 16017
+MACS_PER_FP_MUL = 300
+MACS_PER_PAIRING = FP_MULS_PER_PAIRING * MACS_PER_FP_MUL
+IO_BYTES_PER_PAIRING = 288 + 576
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2-batch", type=int, default=20, help="pairings per GPU per step = 2^this")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+
+def cpu_oracle_rate(n_sample: int, threads: int, seed: int = 0x5EED):
+    """Times the C oracle (oracle/zkp_oracle.c, a port of the reference's CPU path with the
+    reference's tower structure) on n_sample seeded pairings with `threads` host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import coracle
+    import util
+    coracle.build()
+    g1, i1, g2, i2 = util.oracle_points(coracle, seed, 0, n_sample)     # untimed input generation
+    t0 = time.perf_counter()
+    coracle.pairing_batch(g1, None, g2, None, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return n_sample / dt, dt
+
+
+def cpu_baseline(target_seconds: float):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import coracle
+    cores = coracle.ncores()
+    rate, _ = cpu_oracle_rate(8 * cores, cores)                        # calibration
+    n = max(cores, int(rate * target_seconds))
+    n = min(n, 1 << 16)
+    rate, dt = cpu_oracle_rate(n, cores)
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d seeded pairings (a_i*G1, b_i*G2) in %.1f s on %d host threads, C restatement of the reference tower "
+                      "(Montgomery Fp instead of the reference's BigUint)" % (n, dt, cores)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  The Rust crate cannot be built here (no rustc,
+    un-vendored sp1 git dependency) and its src/pairings.rs is empty, so this is the oracle port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import coracle
+    cores = coracle.ncores()
+    rate0, _ = cpu_oracle_rate(8 * cores, cores)
+    # bounded sample per step so that (steps + warmup) stays within a few minutes
+    per_step_s = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    n = max(cores, min(1 << 16, int(rate0 * per_step_s)))
+    for _ in range(args.warmup):
+        cpu_oracle_rate(n, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_oracle_rate(n, cores)
+        t += dt
+    rate = n * args.steps / t
+    sample = "%d seeded pairings per step on %d host threads (bounded sample of the 2^%d workload)" % (n, cores, args.log2_batch)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32-limb integer (Montgomery Fp, 6x64 on CPU)", "data": "synthetic",
+        "config": {"workload": "2^%d independent random BLS12-381 pairings per GPU (CPU arm runs a bounded sample)" % args.log2_batch,
+                   "sample_pairings_per_step": n},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import zkvm_pairings_b200 as z
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the pairing engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = 1 << args.log2_batch
+    eng = z.PairingEngine([local])
+    st = torch.cuda.current_stream().cuda_stream
+    dev = torch.device("cuda", local)
+
+    # ---- synthetic inputs, generated on the device (valid subgroup points), untimed
+    g1 = torch.empty((n, 12), dtype=torch.int64, device=dev)
+    g2 = torch.empty((n, 24), dtype=torch.int64, device=dev)
+    i1 = torch.empty(n, dtype=torch.uint8, device=dev)
+    i2 = torch.empty(n, dtype=torch.uint8, device=dev)
+    out = torch.empty((n, 72), dtype=torch.int64, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    eng.gen_points_dev(0x5EED5EED, rank * n, n, g1, i1, g2, i2, stream=st)
+    torch.cuda.synchronize()
+
+    # ---- integer-multiply roofline denominators, measured in this run
+    peak_wide = eng.imad_peak(0)
+    peak_lo = eng.imad_peak(1)
+    peak_chain = eng.imad_peak(2)
+
+    def step():
+        eng.pairing_dev(z.MODE_PAIRING, out, g1=g1, g2=g2, err=err, stream=st)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = eng.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record()
+    barrier()
+    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[-1])
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+    assert int(err.item()) == 0, "non-canonical synthetic input?"
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    value = world * n * args.steps / (max_ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call, pinned host memory, copies in the timed region
+    e2e_n = n
+    h_g1 = torch.empty((e2e_n, 12), dtype=torch.int64).pin_memory()
+    h_g2 = torch.empty((e2e_n, 24), dtype=torch.int64).pin_memory()
+    h_out = torch.empty((e2e_n, 72), dtype=torch.int64).pin_memory()
+    h_g1.copy_(g1[:e2e_n])
+    h_g2.copy_(g2[:e2e_n])
+    n_g1, n_g2, n_out = h_g1.numpy().view(np.uint64), h_g2.numpy().view(np.uint64), h_out.numpy().view(np.uint64)
+    lib = eng._lib
+    import ctypes
+
+    def p(a):
+        return a.ctypes.data_as(ctypes.c_void_p)
+
+    def e2e_step():
+        rc = lib.zkp_pairing_batch(eng._ctx, p(n_g1), None, p(n_g2), None, e2e_n, p(n_out))
+        assert rc == 0, lib.zkp_last_error()
+
+    e2e_step()                      # warm-up (allocates the pipeline buffers)
+    barrier()
+    e2e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+    te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_n * e2e_steps / float(te.item())
+    # the e2e result must equal the device-resident result (same inputs)
+    same = bool(torch.equal(h_out[:4096], out[:4096].cpu()))
+
+    if rank == 0:
+        per_launch_ms = sum(kernel_ms) / len(kernel_ms)
+        pairs_per_s_kernel = n / (per_launch_ms * 1e-3)
+        achieved = pairs_per_s_kernel * MACS_PER_PAIRING
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32-limb integer (12x32-bit Montgomery Fp)", "data": "synthetic",
+            "config": {"workload": "2^%d independent random BLS12-381 pairings per GPU (a_i*G1gen, b_i*G2gen; Miller loop + final "
+                                   "exponentiation, one fused kernel launch per step)" % args.log2_batch,
+                       "pairings_per_gpu_per_step": n, "parallelism": "independent pairings sharded one slice per GPU, no collective",
+                       "l2": "inputs+outputs per step = %.0f MB > 126 MB L2; kernel is integer-bound, not cache sensitive" % (n * IO_BYTES_PER_PAIRING / 1e6),
+                       "engine": eng.version()},
+            "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak_wide / 1e12, "unit": "T wide-MAC/s",
+                         "frac": achieved / peak_wide, "traffic": None,
+                         "kernel": "k_pairing<1>", "kernel_ms": per_launch_ms, "algorithmic_macs_per_pairing": MACS_PER_PAIRING,
+                         "peak_source": "measured in this run: independent IMAD.WIDE.U32 chains on all SMs (zkp_imad_peak kind 0)",
+                         "peak_imad_lo": peak_lo / 1e12, "peak_carry_chain": peak_chain / 1e12,
+                         "hbm_gbs_achieved": pairs_per_s_kernel * IO_BYTES_PER_PAIRING / 1e9},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_n * 288, "d2h_bytes_per_step": e2e_n * 576,
+                    "steps": e2e_steps, "matches_device_path": same},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,190 @@
+/*
+ * zkpair.h -- C ABI of the B200-native batched BLS12-381 pairing engine (libzkpair.so).
+ *
+ * This is the drop-in boundary for the pairing hot path of 0xWOLAND/zkvm-pairings.  Citations are
+ * into /root/reference/ (the Rust crate being replaced on this path).
+ *
+ * What it replaces
+ *   - the per-operation accelerator boundary the reference has today, the SP1 zkVM precompile FFI
+ *       bls12381_sys_bigint(result:&mut[u32;12], op:u32 /0=mul,1=add/, lhs:&[u32;12], rhs:&[u32;12])   src/fp.rs:376,443
+ *       syscall_bls12381_fp_mulmod(lhs:*mut u32, rhs:*const u32)                                       src/fp.rs:126
+ *     -> zkp_fp_mul_batch / zkp_tower_op_batch (same canonical 12xu32 = 6xu64 little-endian limbs,
+ *        but batched so one call amortises the launch);
+ *   - the tower methods on the path (Fp/Fp2/Fp6/Fp12 mul, square, invert, frobenius_map, conjugate,
+ *     mul_by_1 / mul_by_01 / mul_by_014: src/fp2.rs:147-313, src/fp6.rs:102-309, src/fp12.rs:99-210)
+ *     -> zkp_tower_op_batch with the ZKP_OP_* code of the method;
+ *   - the module the reference declares but leaves EMPTY (src/lib.rs:12, src/pairings.rs = 0 bytes):
+ *     pairing / miller_loop / multi_miller_loop / final_exponentiation and the batch entry points
+ *     the north star adds -> zkp_miller_loop_batch, zkp_final_exp_batch, zkp_pairing_batch,
+ *     zkp_multi_miller_loop_batch, zkp_multi_pairing_batch, zkp_multi_miller_product.
+ *
+ * Conventions
+ *   - Every function returns int32_t: ZKP_OK (0) or a negative ZKP_ERR_* code; zkp_last_error()
+ *     returns a thread-local message.  Nothing panics or aborts.  There is NO CPU fallback: with no
+ *     CUDA device zkp_ctx_create fails with ZKP_ERR_NO_DEVICE.
+ *   - The caller owns every buffer.  Element layout is array-of-structs of canonical (non-
+ *     Montgomery, value in [0,p)) little-endian u64 limbs, exactly `Fp.0` (src/fp.rs:24):
+ *       Fp = 6 u64; Fp2 = c0|c1 (12); Fp6 = c0|c1|c2 (36); Fp12 / Gt = c0|c1 (72 u64 = 576 bytes);
+ *       G1 point = x|y (12 u64), G2 point = x.c0|x.c1|y.c0|y.c1 (24 u64); the `is_infinity` flag of
+ *       G1Affine/G2Affine (src/g1.rs:7-11, src/g2.rs:8-12) travels in a separate uint8_t array
+ *       (NULL = no point is at infinity).  A pair with either point at infinity contributes
+ *       Fp12::one() (zkcrypto lineage behaviour).
+ *   - Inputs with a limb vector >= p are rejected with ZKP_ERR_NONCANONICAL (the reference's neg is
+ *     undefined there, src/fp.rs:383-405); outputs are then unspecified.
+ *   - Host entry points (no suffix) copy host->device, run, copy device->host, and shard the batch
+ *     in contiguous slices over the devices of the context.  *_dev entry points take DEVICE
+ *     pointers valid on device `dev` (an index into the context's device list), enqueue on
+ *     `stream` (a cudaStream_t, NULL = that device's context stream) and return without
+ *     synchronising; their error/status words are device resident.
+ *   - Calls on one zkp_ctx are serialised by an internal mutex; distinct contexts are independent.
+ */
+#ifndef ZKPAIR_H
+#define ZKPAIR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKP_OK 0
+#define ZKP_ERR_INVALID_ARG (-1)
+#define ZKP_ERR_CUDA (-2)
+#define ZKP_ERR_NONCANONICAL (-3)
+#define ZKP_ERR_NO_DEVICE (-4)
+#define ZKP_ERR_TOO_MANY_PAIRS (-5)
+
+#define ZKP_MAX_PAIRS_PER_CHECK 8
+
+/* element-wise tower operations (zkp_tower_op_batch); reference method in the comment */
+enum zkp_tower_op {
+    ZKP_OP_FP_ADD = 0,        /* Fp::add            src/fp.rs:351-368 */
+    ZKP_OP_FP_SUB = 1,        /* Fp::sub            src/fp.rs:407-411 */
+    ZKP_OP_FP_NEG = 2,        /* Fp::neg            src/fp.rs:381-405 */
+    ZKP_OP_FP_MUL = 3,        /* Fp::mul            src/fp.rs:413-434 */
+    ZKP_OP_FP_SQR = 4,        /* Fp::square         src/fp.rs:452-455 */
+    ZKP_OP_FP_INV = 5,        /* Fp::invert         src/fp.rs:306-319 (status bit1 set for zero) */
+    ZKP_OP_FP2_ADD = 16, ZKP_OP_FP2_SUB = 17, ZKP_OP_FP2_NEG = 18,
+    ZKP_OP_FP2_MUL = 19,      /* src/fp2.rs:192-209 */
+    ZKP_OP_FP2_SQR = 20,      /* src/fp2.rs:171-189 */
+    ZKP_OP_FP2_INV = 21,      /* src/fp2.rs:278-296 */
+    ZKP_OP_FP2_MUL_NR = 22,   /* mul_by_nonresidue  src/fp2.rs:161-168 */
+    ZKP_OP_FP2_CONJ = 23,     /* conjugate = frobenius_map  src/fp2.rs:147-157 */
+    ZKP_OP_FP6_ADD = 32, ZKP_OP_FP6_SUB = 33, ZKP_OP_FP6_NEG = 34,
+    ZKP_OP_FP6_MUL = 35,      /* src/fp6.rs:188-267 */
+    ZKP_OP_FP6_SQR = 36,      /* src/fp6.rs:274-288 */
+    ZKP_OP_FP6_INV = 37,      /* src/fp6.rs:291-309 */
+    ZKP_OP_FP6_MUL_NR = 38,   /* src/fp6.rs:128-139 */
+    ZKP_OP_FP6_FROB = 39,     /* TRUE a^p; src/fp6.rs:142-176 has wrong constants */
+    ZKP_OP_FP6_MUL_BY_1 = 40, /* b = c1 (Fp2)            src/fp6.rs:102-108 */
+    ZKP_OP_FP6_MUL_BY_01 = 41,/* b = c0|c1 (2 Fp2)       src/fp6.rs:110-125 */
+    ZKP_OP_FP12_ADD = 48, ZKP_OP_FP12_SUB = 49, ZKP_OP_FP12_NEG = 50,
+    ZKP_OP_FP12_MUL = 51,     /* src/fp12.rs:193-210 */
+    ZKP_OP_FP12_SQR = 52,     /* src/fp12.rs:173-184 */
+    ZKP_OP_FP12_INV = 53,     /* src/fp12.rs:186-190 */
+    ZKP_OP_FP12_CONJ = 54,    /* src/fp12.rs:123-125 */
+    ZKP_OP_FP12_FROB = 55,    /* TRUE a^p (src/fp12.rs:143-170 inherits the Fp6 defect) */
+    ZKP_OP_FP12_MUL_BY_014 = 56, /* b = c0|c1|c4 (3 Fp2) src/fp12.rs:99-111 */
+    ZKP_OP_FP12_CYC_SQR = 57, /* Granger-Scott cyclotomic squaring */
+    ZKP_OP_FP12_CYC_EXP = 58, /* f^x for the curve parameter x (negative): conj(f^|x|) */
+    ZKP_OP_FP12_FROB2 = 59,   /* a^(p^2) */
+    ZKP_OP_FP12_FROB3 = 60    /* a^(p^3) */
+};
+
+typedef struct zkp_ctx zkp_ctx;
+
+/* ---- context ------------------------------------------------------------------------------ */
+
+/* Number of CUDA devices visible (0 when there is none / no driver). */
+int32_t zkp_device_count(void);
+/* devices == NULL or n_devices <= 0: use every visible device.  Fails with ZKP_ERR_NO_DEVICE when
+ * no CUDA device is usable (there is no CPU path). */
+int32_t zkp_ctx_create(const int *devices, int n_devices, zkp_ctx **out);
+void zkp_ctx_destroy(zkp_ctx *ctx);
+int32_t zkp_ctx_num_devices(const zkp_ctx *ctx);
+/* Thread-local description of the last error returned to this thread. */
+const char *zkp_last_error(void);
+/* Library / build description string (arch, launch geometry). */
+const char *zkp_version(void);
+
+/* ---- tower operations (parity / test surface for the tower rows of SURVEY 8a) -------------- */
+
+/* out[i] = op(a[i], b[i]).  b may be NULL for unary ops.  status (optional, n bytes): bit0 =
+ * non-canonical input, bit1 = inverse of zero requested (the reference returns None; out = 0). */
+int32_t zkp_tower_op_batch(zkp_ctx *ctx, int32_t op, const uint64_t *a, const uint64_t *b,
+                           uint64_t *out, uint8_t *status, size_t n);
+/* Named wrappers for the three ops SURVEY 8b lists. */
+int32_t zkp_fp_mul_batch(zkp_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+int32_t zkp_fp12_mul_batch(zkp_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+int32_t zkp_fp12_mul_by_014_batch(zkp_ctx *ctx, const uint64_t *f, const uint64_t *c0_c1_c4,
+                                  uint64_t *out, size_t n);
+
+/* ---- pairing path (host buffers) ---------------------------------------------------------- */
+
+/* n independent Miller loops: out_fp12[i] = miller_loop(G1[i], G2[i])   (SURVEY 9.1 convention) */
+int32_t zkp_miller_loop_batch(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_inf,
+                              const uint64_t *g2_xy, const uint8_t *g2_inf, size_t n, uint64_t *out_fp12);
+/* out_fp12[i] = in_fp12[i]^((p^12-1)/r) */
+int32_t zkp_final_exp_batch(zkp_ctx *ctx, const uint64_t *in_fp12, size_t n, uint64_t *out_fp12);
+/* out_gt[i] = e(G1[i], G2[i]) */
+int32_t zkp_pairing_batch(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_inf,
+                          const uint64_t *g2_xy, const uint8_t *g2_inf, size_t n, uint64_t *out_gt);
+/* n_checks checks of pairs_per_check (<= ZKP_MAX_PAIRS_PER_CHECK) pairs each, stored check-major;
+ * every check runs ONE shared-accumulator Miller loop over its pairs. */
+int32_t zkp_multi_miller_loop_batch(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_inf,
+                                    const uint64_t *g2_xy, const uint8_t *g2_inf, size_t n_checks,
+                                    int32_t pairs_per_check, uint64_t *out_fp12);
+/* ... followed by one final exponentiation per check.  out_is_one (optional, n_checks bytes) is 1
+ * where the product of pairings equals Gt one (e.g. a Groth16 verification equation holds). */
+int32_t zkp_multi_pairing_batch(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_inf,
+                                const uint64_t *g2_xy, const uint8_t *g2_inf, size_t n_checks,
+                                int32_t pairs_per_check, uint64_t *out_gt, uint8_t *out_is_one);
+/* prod_i e(G1[i], G2[i]) for one large product: per-device Miller loops over a contiguous slice,
+ * per-device Fp12 partial product, gather of the 576-byte partials to the first device, multiply,
+ * ONE final exponentiation.  out_miller_product (optional) receives the un-exponentiated product. */
+int32_t zkp_multi_miller_product(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_inf,
+                                 const uint64_t *g2_xy, const uint8_t *g2_inf, size_t n,
+                                 uint64_t *out_miller_product, uint64_t *out_gt);
+
+/* ---- device-resident entry points (asynchronous; pointers are device pointers on `dev`) ---- */
+
+/* mode: 1 = Miller loop only, 2 = final exponentiation only (d_in_fp12 -> d_out), 3 = pairing.
+ * d_err (optional): device uint32_t that is OR-ed with 1 when an input is non-canonical. */
+int32_t zkp_pairing_dev(zkp_ctx *ctx, int32_t dev, int32_t mode, const uint64_t *d_g1_xy,
+                        const uint8_t *d_g1_inf, const uint64_t *d_g2_xy, const uint8_t *d_g2_inf,
+                        size_t n_checks, int32_t pairs_per_check, const uint64_t *d_in_fp12,
+                        uint64_t *d_out, uint8_t *d_is_one, uint32_t *d_err, void *stream);
+int32_t zkp_tower_op_dev(zkp_ctx *ctx, int32_t dev, int32_t op, const uint64_t *d_a, const uint64_t *d_b,
+                         uint64_t *d_out, uint8_t *d_status, uint32_t *d_err, size_t n, void *stream);
+/* d_out (72 u64) = product of the n Fp12 elements at d_in (canonical limbs); d_scratch must hold
+ * zkp_product_scratch_elems(n) * 72 u64. */
+size_t zkp_product_scratch_elems(size_t n);
+int32_t zkp_fp12_product_dev(zkp_ctx *ctx, int32_t dev, const uint64_t *d_in, size_t n,
+                             uint64_t *d_scratch, uint64_t *d_out, uint32_t *d_err, void *stream);
+/* Synthetic valid inputs: G1[i] = a_i * G1gen, G2[i] = b_i * G2gen with 64-bit scalars
+ * a_i = splitmix64(seed, 2*(first+i)), b_i = splitmix64(seed, 2*(first+i)+1) (zero mapped to 1). */
+int32_t zkp_gen_points_dev(zkp_ctx *ctx, int32_t dev, uint64_t seed, uint64_t first, size_t n,
+                           uint64_t *d_g1_xy, uint8_t *d_g1_inf, uint64_t *d_g2_xy, uint8_t *d_g2_inf,
+                           void *stream);
+/* Host-buffer version of the generator. */
+int32_t zkp_gen_points(zkp_ctx *ctx, uint64_t seed, uint64_t first, size_t n, uint64_t *g1_xy,
+                       uint8_t *g1_inf, uint64_t *g2_xy, uint8_t *g2_inf);
+
+/* ---- measurement helpers -------------------------------------------------------------------- */
+
+/* Integer-multiply roofline probe: runs independent IMAD.WIDE.U32 (kind 0), IMAD lo (kind 1) or
+ * carry-chained IMAD.WIDE.U32.X (kind 2) chains on every SM of device `dev` and reports the
+ * sustained rate in multiply-accumulates per second (CUDA-event timed). */
+int32_t zkp_imad_peak(zkp_ctx *ctx, int32_t dev, int32_t kind, double *macs_per_second);
+/* Number of kernel launches issued by this context so far (for bench.py's gpu_launches). */
+uint64_t zkp_launch_count(const zkp_ctx *ctx);
+/* Name and average duration (ms, CUDA events on the launching stream) of the most recent timed
+ * pairing-path kernel on device `dev`; timing is enabled with zkp_set_kernel_timing(ctx, 1). */
+int32_t zkp_set_kernel_timing(zkp_ctx *ctx, int32_t enabled);
+int32_t zkp_last_kernel_ms(zkp_ctx *ctx, int32_t dev, double *total_ms, uint64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKPAIR_H */

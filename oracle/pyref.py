@@ -512,6 +512,8 @@ def g1_add(p, q):          # src/g1.rs:155-187 ; P + (-P) panics in the referenc
     x2, y2, _ = q
     if x1 == x2 and y1 == y2:
         return g1_double(p)
+    if x1 == x2:               # P + (-P): the reference divides by zero and panics (src/g1.rs:177);
+        return G1_IDENTITY     # the oracle returns the identity so r*G = O can be exercised
     slope = fp_div(fp_sub(y2, y1), fp_sub(x2, x1))
     xr = fp_sub(fp_sub(fp_square(slope), x1), x2)
     yr = fp_sub(fp_mul(slope, fp_sub(x1, xr)), y1)
@@ -583,6 +585,8 @@ def g2_add(p, q):          # src/g2.rs:210-242
     x2, y2, _ = q
     if x1 == x2 and y1 == y2:
         return g2_double(p)
+    if x1 == x2:               # P + (-P): reference panics (src/g2.rs:232); oracle returns identity
+        return G2_IDENTITY
     slope = fp2_div(fp2_sub(y2, y1), fp2_sub(x2, x1))
     xr = fp2_sub(fp2_sub(fp2_square(slope), x1), x2)
     yr = fp2_sub(fp2_mul(slope, fp2_sub(x1, xr)), y1)

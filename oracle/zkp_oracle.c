@@ -418,6 +418,8 @@ static void g1_add(g1a *r, const g1a *p, const g1a *q) { /* src/g1.rs:155-187 */
     if (p->inf) { *r = *q; return; }
     if (q->inf) { *r = *p; return; }
     if (fp_eq(&p->x, &q->x) && fp_eq(&p->y, &q->y)) { g1_double(r, p); return; }
+    /* P + (-P): the reference divides by zero and panics (src/g1.rs:177); return the identity */
+    if (fp_eq(&p->x, &q->x)) { memset(r, 0, sizeof *r); r->y = R1; r->inf = 1; return; }
     fp n, d, s, xr, yr, t;
     fp_sub(&n, &q->y, &p->y); fp_sub(&d, &q->x, &p->x);
     fp_inv(&d, &d); fp_mul(&s, &n, &d);
@@ -439,6 +441,7 @@ static void g2_add(g2a *r, const g2a *p, const g2a *q) { /* src/g2.rs:210-242 */
     if (p->inf) { *r = *q; return; }
     if (q->inf) { *r = *p; return; }
     if (fp2_eq(&p->x, &q->x) && fp2_eq(&p->y, &q->y)) { g2_double(r, p); return; }
+    if (fp2_eq(&p->x, &q->x)) { memset(r, 0, sizeof *r); r->y.c0 = R1; r->inf = 1; return; } /* src/g2.rs:232 panics */
     fp2 n, d, s, xr, yr, t;
     fp2_sub(&n, &q->y, &p->y); fp2_sub(&d, &q->x, &p->x);
     fp2_inv(&d, &d); fp2_mul(&s, &n, &d);

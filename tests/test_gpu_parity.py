@@ -1,0 +1,255 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(libzkpair.so), against the CPU oracle on identical seeded inputs, against the committed golden
+vectors, and -- at BASELINE.json's full batch sizes -- through size-independent properties
+(bilinearity, product checks, Miller-product consistency).  Bit-exact everywhere (integer path)."""
+import os
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+VEC = util.golden("pairing_vectors.json")
+FULL = int(os.environ.get("ZKP_TEST_FULL_LOG2", "16"))     # BASELINE config[1]: 2^16 pairings
+
+
+def _cases():
+    cases = VEC["pairings"]
+    g1 = np.stack([util.g1_to_arr(util.hex_g1(c["g1"])) for c in cases])
+    g2 = np.stack([util.g2_to_arr(util.hex_g2(c["g2"])) for c in cases])
+    i1 = np.array([c["g1"]["inf"] for c in cases], dtype=np.uint8)
+    i2 = np.array([c["g2"]["inf"] for c in cases], dtype=np.uint8)
+    return cases, g1, i1, g2, i2
+
+
+def test_native_library_is_the_one_loaded(engine):
+    from zkvm_pairings_b200 import _lib
+    assert os.path.samefile(_lib.lib_path(), os.path.join(os.path.dirname(_lib.__file__), "libzkpair.so"))
+    with open("/proc/self/maps") as f:
+        assert "libzkpair.so" in f.read()
+    assert "sm_100a" in engine.version()
+    before = engine.launch_count
+    engine.fp_mul_batch(util.fp_arr([3]), util.fp_arr([5]))
+    assert engine.launch_count == before + 1
+
+
+def test_fp_mul_known_answers(engine, pyref):
+    P = pyref.P
+    vals = [0, 1, 2, P - 1, P - 2, pyref.R_MONT, P // 2, (1 << 380) + 12345]
+    a = util.fp_arr([x for x in vals for _ in vals]).reshape(-1, 6)
+    b = util.fp_arr([y for _ in vals for y in vals]).reshape(-1, 6)
+    out = engine.fp_mul_batch(a, b)
+    assert util.arr_fp(out) == [x * y % P for x in vals for y in vals]
+
+
+@pytest.mark.parametrize("name", sorted(__import__("zkvm_pairings_b200").TOWER_OPS))
+def test_tower_op_matches_oracle(engine, coracle, name):
+    from zkvm_pairings_b200 import TOWER_OPS, op_widths
+    na, nb, nr = op_widths(name)
+    n = 1000 if not name.endswith(("_inv", "cyc_exp")) else 200
+    a = util.random_fp_matrix(n, na, seed=TOWER_OPS[name] + 1)
+    b = util.random_fp_matrix(n, nb, seed=TOWER_OPS[name] + 101) if nb else None
+    out, status = engine.tower_op(name, a, b, return_status=True)
+    if name in ("fp12_frob2", "fp12_frob3"):
+        exp = a
+        for _ in range(int(name[-1])):
+            exp = coracle.tower_op("fp12_frob", exp)
+    else:
+        exp = coracle.tower_op(name, a, b)
+    assert np.array_equal(out, exp)
+    assert not (status & 1).any()
+    if name.endswith("_inv"):
+        assert status[0] == 2 and not status[3:].any()
+
+
+def test_empty_and_ragged_batches(engine, coracle):
+    assert engine.fp_mul_batch(np.zeros((0, 6), np.uint64), np.zeros((0, 6), np.uint64)).shape == (0, 6)
+    assert engine.pairing_batch(np.zeros((0, 12), np.uint64), np.zeros((0, 24), np.uint64)).shape == (0, 72)
+    for n in (1, 31, 33, 129):     # not multiples of the warp / block size
+        g1, i1, g2, i2 = util.oracle_points(coracle, 99, 0, n)
+        assert np.array_equal(engine.miller_loop_batch(g1, g2), coracle.miller_loop_batch(g1, None, g2, None))
+    with pytest.raises(ValueError):
+        engine.multi_pairing_batch(np.zeros((5, 12), np.uint64), np.zeros((5, 24), np.uint64), 4)
+
+
+def test_noncanonical_inputs_rejected(engine, pyref):
+    from zkvm_pairings_b200 import NonCanonicalError
+    g1 = util.g1_to_arr(pyref.G1_GENERATOR)[None].copy()
+    g2 = util.g2_to_arr(pyref.G2_GENERATOR)[None]
+    g1[0, 6:12] = util.fp_arr([pyref.P])
+    with pytest.raises(NonCanonicalError):
+        engine.pairing_batch(g1, g2)
+    out, status = engine.tower_op("fp_neg", util.fp_arr([pyref.P - 1]), return_status=True)
+    assert status[0] == 0
+    with pytest.raises(NonCanonicalError):
+        engine.tower_op("fp_neg", util.fp_arr([pyref.P]))
+    # the context stays usable after an error
+    assert util.arr_fp(engine.fp_mul_batch(util.fp_arr([3]), util.fp_arr([5]))) == [15]
+
+
+def test_pairing_golden_vectors(engine, pyref):
+    cases, g1, i1, g2, i2 = _cases()
+    ml = engine.miller_loop_batch(g1, g2, i1, i2)
+    gt = engine.pairing_batch(g1, g2, i1, i2)
+    for k, c in enumerate(cases):
+        assert util.arr_to_fp12(ml[k]) == util.hex_fp12(c["miller_loop"]), k
+        assert util.arr_to_fp12(gt[k]) == util.hex_fp12(c["pairing"]), k
+    gen = util.golden("pairing_vectors.json")["generators"]
+    e = engine.pairing_batch(util.g1_to_arr(pyref.G1_GENERATOR), util.g2_to_arr(pyref.G2_GENERATOR))
+    assert pyref.fp12_sha256(util.arr_to_fp12(e[0])) == gen["pairing_sha256"] == "06fa588b89fdfb034dbc1c163ecb3dfac228f552b643c7294cc5f2c4dc170b84"
+    m = engine.miller_loop_batch(util.g1_to_arr(pyref.G1_GENERATOR), util.g2_to_arr(pyref.G2_GENERATOR))
+    assert pyref.fp12_sha256(util.arr_to_fp12(m[0])) == "eceb6467936a62ed011881c3efceb3b9f05b6017afd264fa0caeebf4f8437115"
+    assert np.array_equal(engine.final_exponentiation_batch(ml), gt)
+    # infinity on either side gives Gt one (last two golden cases)
+    assert util.arr_to_fp12(gt[-1]) == pyref.FP12_ONE and util.arr_to_fp12(gt[-2]) == pyref.FP12_ONE
+
+
+def test_bilinearity_config0(engine, pyref):
+    """BASELINE config[0]: e(aP, bQ) == e(P, Q)^(ab), with aP, bQ made by the ORACLE."""
+    o = pyref
+    e = util.arr_to_fp12(engine.pairing_batch(util.g1_to_arr(o.G1_GENERATOR), util.g2_to_arr(o.G2_GENERATOR))[0])
+    for a, b in ((6, 11), (5, 7), (2, 3)):
+        p, q = o.g1_mul(o.G1_GENERATOR, a), o.g2_mul(o.G2_GENERATOR, b)
+        got = util.arr_to_fp12(engine.pairing_batch(util.g1_to_arr(p), util.g2_to_arr(q))[0])
+        assert got == o.fp12_pow_int(e, a * b)
+
+
+def test_point_generator_matches_oracle(engine, coracle):
+    n = 300
+    g1, i1, g2, i2 = engine.gen_points(0x5EED, 1000, n)
+    e1, ei1, e2, ei2 = util.oracle_points(coracle, 0x5EED, 1000, n)
+    assert np.array_equal(g1, e1) and np.array_equal(g2, e2)
+    assert not i1.any() and not i2.any()
+
+
+def test_batch_matches_oracle_seeded(engine, coracle):
+    n = 2048
+    g1, i1, g2, i2 = util.oracle_points(coracle, 0xC0FFEE, 0, n)
+    i1[5] = 1
+    i2[9] = 1
+    assert np.array_equal(engine.miller_loop_batch(g1, g2, i1, i2), coracle.miller_loop_batch(g1, i1, g2, i2))
+    gt = engine.pairing_batch(g1, g2, i1, i2)
+    assert np.array_equal(gt, coracle.pairing_batch(g1, i1, g2, i2))
+
+
+def test_multi_pairing_checks(engine, coracle, pyref):
+    for chk in VEC["multi"]:
+        a1 = np.stack([util.g1_to_arr(util.hex_g1(x["g1"])) for x in chk["pairs"]])
+        a2 = np.stack([util.g2_to_arr(util.hex_g2(x["g2"])) for x in chk["pairs"]])
+        out, one = engine.multi_pairing_batch(a1, a2, 4)
+        assert util.arr_to_fp12(out[0]) == util.hex_fp12(chk["gt"]) and bool(one[0]) == chk["is_one"]
+        mm = engine.multi_miller_loop_batch(a1, a2, 4)
+        assert util.arr_to_fp12(mm[0]) == util.hex_fp12(chk["multi_miller"])
+    # random checks of every supported width, with some infinities, vs the oracle
+    for k in (1, 2, 3, 4, 5, 8):
+        nchk = 40
+        g1, i1, g2, i2 = util.oracle_points(coracle, 1234 + k, 0, nchk * k)
+        i1[3] = 1
+        out, one = engine.multi_pairing_batch(g1, g2, k, i1, i2)
+        exp, eone = coracle.multi_pairing_batch(g1, i1, g2, i2, k)
+        assert np.array_equal(out, exp) and np.array_equal(one, eone), k
+    from zkvm_pairings_b200 import ZkpError
+    with pytest.raises(ZkpError):
+        engine.multi_pairing_batch(np.zeros((9, 12), np.uint64), np.zeros((9, 24), np.uint64), 9)
+
+
+def test_groth16_style_checks_config3_small(engine, coracle, pyref):
+    """4-pair checks e(A,B) e(-alpha,beta) e(-C,delta) e(-L,gamma): valid => one; 1% corrupted."""
+    o = pyref
+    nchk = 256
+    rng = np.random.default_rng(3)
+    sc = rng.integers(1, 1 << 20, size=(nchk, 6)).astype(object)
+    k1, k2, bad = [], [], []
+    for i in range(nchk):
+        a, b, c, d, l, g = (int(x) for x in sc[i])
+        # choose alpha*beta so the exponents cancel:  a*b - al*be - c*d - l*g = 0  (mod r)
+        al, be = 1, (a * b - c * d - l * g) % o.R_ORDER
+        corrupt = (i % 100) == 7
+        bad.append(corrupt)
+        if corrupt:
+            l += 1
+        k1 += [a, o.R_ORDER - al, o.R_ORDER - c, o.R_ORDER - l]
+        k2 += [b, be, d, g]
+    g1, i1 = coracle.g1_mul_batch(util.scalar_matrix(k1))
+    g2, i2 = coracle.g2_mul_batch(util.scalar_matrix(k2))
+    out, one = engine.multi_pairing_batch(g1, g2, 4, i1, i2)
+    assert [not bool(x) for x in one] == bad
+    exp, eone = coracle.multi_pairing_batch(g1, i1, g2, i2, 4)
+    assert np.array_equal(out, exp) and np.array_equal(one, eone)
+
+
+def test_multi_miller_product(engine, coracle):
+    n = 700
+    g1, i1, g2, i2 = util.oracle_points(coracle, 77, 0, n)
+    ml, gt = engine.multi_miller_product(g1, g2)
+    eml, egt = coracle.miller_product(g1, None, g2, None)
+    assert np.array_equal(ml, eml) and np.array_equal(gt, egt)
+
+
+def test_full_size_config1_bit_exact(engine, coracle):
+    """BASELINE config[1]: 2^16 independent pairings, every Gt bit-exact against the oracle."""
+    n = 1 << FULL
+    g1, i1, g2, i2 = engine.gen_points(0x5EED5EED, 0, n)
+    gt = engine.pairing_batch(g1, g2)
+    step = max(1, n // (1 << 13)) if coracle.ncores() < 16 else 1    # whole batch when the host has the cores
+    idx = np.arange(0, n, step)
+    assert np.array_equal(gt[idx], coracle.pairing_batch(g1[idx], None, g2[idx], None))
+    # size-independent property over the WHOLE batch: product of all Miller loops through the sharded
+    # product path equals the product of the per-pair outputs
+    ml = engine.miller_loop_batch(g1, g2)
+    prod, gt_prod = engine.multi_miller_product(g1, g2)
+    import torch
+    d_in = torch.from_numpy(ml.view(np.int64)).cuda()
+    scratch = torch.empty(engine.product_scratch_elems(n) * 72, dtype=torch.int64, device="cuda")
+    d_out = torch.empty(72, dtype=torch.int64, device="cuda")
+    engine.fp12_product_dev(d_in, n, scratch, d_out, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint64), prod)
+    assert np.array_equal(engine.final_exponentiation_batch(prod[None])[0], gt_prod)
+
+
+def test_full_size_final_exp_config2_properties(engine, coracle, pyref):
+    """BASELINE config[2] shape (final exponentiation only) at 2^16 here: outputs lie in the order-r
+    subgroup (checked on a sample via the oracle) and f -> f^2 commutes with the map."""
+    n = 1 << min(FULL, 16)
+    g1, i1, g2, i2 = engine.gen_points(0xABCDEF, 0, n)
+    ml = engine.miller_loop_batch(g1, g2)
+    fe = engine.final_exponentiation_batch(ml)
+    sq = engine.tower_op("fp12_sqr", ml)
+    fe_sq = engine.final_exponentiation_batch(sq)
+    assert np.array_equal(fe_sq, engine.tower_op("fp12_sqr", fe))
+    for j in (0, n // 2, n - 1):
+        assert pyref.fp12_pow_int(util.arr_to_fp12(fe[j]), pyref.R_ORDER) == pyref.FP12_ONE
+    idx = np.arange(0, n, max(1, n // 512))
+    assert np.array_equal(fe[idx], coracle.final_exp_batch(ml[idx]))
+
+
+def test_device_resident_path(engine, coracle):
+    import torch
+    n = 512
+    g1, i1, g2, i2 = util.oracle_points(coracle, 4242, 0, n)
+    st = torch.cuda.current_stream().cuda_stream
+    dg1, dg2 = torch.from_numpy(g1.view(np.int64)).cuda(), torch.from_numpy(g2.view(np.int64)).cuda()
+    out = torch.empty((n, 72), dtype=torch.int64, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    engine.pairing_dev(3, out, g1=dg1, g2=dg2, err=err, stream=st)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    assert np.array_equal(out.cpu().numpy().view(np.uint64), coracle.pairing_batch(g1, None, g2, None))
+    # generator on device == generator through host buffers
+    a1 = torch.empty((n, 12), dtype=torch.int64, device="cuda")
+    a2 = torch.empty((n, 24), dtype=torch.int64, device="cuda")
+    f1 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    f2 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    engine.gen_points_dev(4242, 0, n, a1, f1, a2, f2, stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(a1.cpu().numpy().view(np.uint64), g1) and np.array_equal(a2.cpu().numpy().view(np.uint64), g2)
+
+
+def test_imad_peak_probe(engine):
+    wide = engine.imad_peak(0)
+    lo = engine.imad_peak(1)
+    chain = engine.imad_peak(2)
+    assert 1e12 < wide < 1e14 and 1e12 < lo < 1e14 and 1e12 < chain < 1e14

@@ -1,0 +1,197 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/zkpair.h
+declares, fails loudly without a GPU (no CPU fallback), the generated constants agree with the
+oracle, and the device code -- compiled as plain C++ with the PTX carry flag emulated
+(tests/host_sim/sim.cpp, a DEV SIMULATION, never part of the product) -- is bit-exact against the
+oracle for every tower op, the Miller loop, the final exponentiation and the point generator."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from zkvm_pairings_b200 import _lib, build
+    build.build()
+    return _lib.load()
+
+
+def test_abi_exports_every_declared_symbol(lib):
+    from zkvm_pairings_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "zkpair.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(zkp_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.zkp_version()
+
+
+def test_no_cuda_device_fails_loudly(lib):
+    """Without a GPU the product path must raise -- never fall back to a CPU implementation."""
+    import zkvm_pairings_b200 as z
+    if z.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(z.ZkpError) as ei:
+        z.PairingEngine()
+    assert ei.value.code == -4
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "zkvm_pairings_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "coracle" not in text and "pyref" not in text and "zkp_oracle" not in text, f
+                assert "host_sim" not in text or f in ("fp.cuh", "ops.cuh"), f   # only comments pointing at the test sim
+
+
+def test_generated_constants_match_oracle(pyref, coracle):
+    o = pyref
+    text = open(os.path.join(ROOT, "zkvm_pairings_b200", "csrc", "consts.cuh")).read()
+
+    def arr(name):
+        m = re.search(r"%s\[\d+\] = \{(.*?)\};" % name, text, re.S)
+        w = [int(x, 16) for x in re.findall(r"0x([0-9a-f]{8})u", m.group(1))]
+        return [sum(w[12 * i + j] << (32 * j) for j in range(12)) for i in range(len(w) // 12)]
+
+    R = o.R_MONT
+    assert arr("ZKP_P") == [o.P] and arr("ZKP_ONE") == [R] and arr("ZKP_R2") == [R * R % o.P]
+    r2, f61, f62, f121 = coracle.constants()
+    assert util.arr_fp(r2)[0] == R * R % o.P
+    frob = arr("ZKP_FROB")
+    unmont = lambda v: v * pow(R, -1, o.P) % o.P
+    g = [(unmont(frob[2 * i]), unmont(frob[2 * i + 1])) for i in range(15)]
+    assert g[0] == o.FROB12_C1 and g[1] == o.FROB6_C1 and g[3] == o.FROB6_C2      # gamma_{1,1}, gamma_{1,2}, gamma_{1,4}
+    assert tuple(util.arr_fp(f121)) == g[0] and tuple(util.arr_fp(f61)) == g[1] and tuple(util.arr_fp(f62)) == g[3]
+    for k in (1, 2, 3):
+        base = o.fp2_pow_vartime((1, 1), o._to_limbs((o.P ** k - 1) // 6, 6 * k))
+        acc = o.FP2_ONE
+        for i in range(5):
+            acc = o.fp2_mul(acc, base)
+            assert g[5 * (k - 1) + i] == acc
+    assert [unmont(v) for v in arr("ZKP_G1_GEN")] == [o.G1_X, o.G1_Y]
+    assert [unmont(v) for v in arr("ZKP_G2_GEN")] == [o.G2_X0, o.G2_X1, o.G2_Y0, o.G2_Y1]
+    assert [unmont(v) for v in arr("ZKP_PSI")] == [o.PSI_COEFF_X[0], o.PSI_COEFF_X[1], o.PSI_COEFF_Y[0], o.PSI_COEFF_Y[1]]
+    assert [unmont(v) for v in arr("ZKP_BETA")] == [o.BETA]
+
+
+def test_op_widths():
+    from zkvm_pairings_b200 import op_widths
+    assert op_widths("fp_mul") == (1, 1, 1) and op_widths("fp_inv") == (1, 0, 1)
+    assert op_widths("fp12_mul_by_014") == (12, 6, 12) and op_widths("fp6_mul_by_01") == (6, 4, 6)
+    assert op_widths("fp12_frob2") == (12, 0, 12) and op_widths("fp2_mul_nr") == (2, 0, 2)
+
+
+# ---------------------------------------------------------------- dev simulation of the device code
+
+@pytest.fixture(scope="module")
+def sim():
+    d = os.path.join(ROOT, "tests", "host_sim")
+    so = os.path.join(d, "libzkpair_sim.so")
+    src = [os.path.join(d, "sim.cpp")] + [os.path.join(ROOT, "zkvm_pairings_b200", "csrc", f)
+                                          for f in ("fp.cuh", "tower.cuh", "pairing.cuh", "ops.cuh", "consts.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src[0]])
+    return ctypes.CDLL(so)
+
+
+def test_sim_tower_ops_bit_exact(sim, coracle):
+    from zkvm_pairings_b200 import TOWER_OPS, op_widths
+    for name, code in TOWER_OPS.items():
+        na, nb, nr = op_widths(name)
+        n = 14
+        a = util.random_fp_matrix(n, na, seed=code + 1)
+        b = util.random_fp_matrix(n, nb, seed=code + 101) if nb else None
+        out = np.zeros((n, 6 * nr), np.uint64)
+        st = np.zeros(n, np.uint8)
+        sim.sim_tower_op(code, _p(a), _p(b), _p(out), _p(st), ctypes.c_size_t(n))
+        if name in ("fp12_frob2", "fp12_frob3"):
+            exp = a
+            for _ in range(int(name[-1])):
+                exp = coracle.tower_op("fp12_frob", exp)
+        else:
+            exp = coracle.tower_op(name, a, b)
+        assert np.array_equal(out, exp), name
+        assert not (st & 1).any()
+        if name.endswith("_inv"):
+            assert st[0] == 2 and not st[3:].any()   # row 0 is all-zero: inverse of zero flagged
+
+
+def test_sim_montgomery_edge_operands(sim, coracle, pyref):
+    """Operands at the bounds the lazy-reduction analysis in fp.cuh relies on."""
+    P = pyref.P
+    vals = [0, 1, P - 1, P - 2, (1 << 381) - 1 if (1 << 381) - 1 < P else P - 3, pyref.R_MONT, P // 2, P // 3]
+    a = util.fp_arr([x for x in vals for _ in vals]).reshape(-1, 6)
+    b = util.fp_arr([y for _ in vals for y in vals]).reshape(-1, 6)
+    out = np.zeros_like(a)
+    sim.sim_tower_op(3, _p(a), _p(b), _p(out), None, ctypes.c_size_t(a.shape[0]))
+    assert util.arr_fp(out) == [x * y % P for x in vals for y in vals]
+
+
+def test_sim_rejects_noncanonical(sim, pyref):
+    a = util.fp_arr([pyref.P, pyref.P + 5, (1 << 384) - 1, pyref.P - 1]).reshape(-1, 6)
+    out, st = np.zeros_like(a), np.zeros(4, np.uint8)
+    sim.sim_tower_op(2, _p(a), None, _p(out), _p(st), ctypes.c_size_t(4))
+    assert list(st & 1) == [1, 1, 1, 0]
+
+
+def test_sim_pairing_golden_vectors(sim, pyref):
+    vec = util.golden("pairing_vectors.json")
+    cases = vec["pairings"]
+    g1 = np.stack([util.g1_to_arr(util.hex_g1(c["g1"])) for c in cases])
+    g2 = np.stack([util.g2_to_arr(util.hex_g2(c["g2"])) for c in cases])
+    i1 = np.array([c["g1"]["inf"] for c in cases], dtype=np.uint8)
+    i2 = np.array([c["g2"]["inf"] for c in cases], dtype=np.uint8)
+    n = len(cases)
+    ml, gt = np.zeros((n, 72), np.uint64), np.zeros((n, 72), np.uint64)
+    assert sim.sim_pairing(1, _p(g1), _p(i1), _p(g2), _p(i2), ctypes.c_size_t(n), 1, None, _p(ml), None) == 0
+    assert sim.sim_pairing(3, _p(g1), _p(i1), _p(g2), _p(i2), ctypes.c_size_t(n), 1, None, _p(gt), None) == 0
+    fe = np.zeros((n, 72), np.uint64)
+    assert sim.sim_pairing(2, None, None, None, None, ctypes.c_size_t(n), 1, _p(ml), _p(fe), None) == 0
+    for k, c in enumerate(cases):
+        assert util.arr_to_fp12(ml[k]) == util.hex_fp12(c["miller_loop"]), k
+        assert util.arr_to_fp12(gt[k]) == util.hex_fp12(c["pairing"]), k
+    assert np.array_equal(fe, gt)
+    assert pyref.fp12_sha256(util.arr_to_fp12(gt[0])) != ""
+    for chk in vec["multi"]:
+        a1 = np.stack([util.g1_to_arr(util.hex_g1(x["g1"])) for x in chk["pairs"]])
+        a2 = np.stack([util.g2_to_arr(util.hex_g2(x["g2"])) for x in chk["pairs"]])
+        out, one = np.zeros((1, 72), np.uint64), np.zeros(1, np.uint8)
+        assert sim.sim_pairing(3, _p(a1), None, _p(a2), None, ctypes.c_size_t(1), 4, None, _p(out), _p(one)) == 0
+        assert util.arr_to_fp12(out[0]) == util.hex_fp12(chk["gt"]) and bool(one[0]) == chk["is_one"]
+
+
+def test_sim_point_generator_matches_oracle(sim, coracle):
+    seed, first, n = 0x5EED, 7, 6
+    a, b = util.scalars_for(seed, first, n)
+    sim.sim_splitmix64_at.restype = ctypes.c_uint64
+    assert sim.sim_splitmix64_at(ctypes.c_uint64(seed), ctypes.c_uint64(2 * first)) == a[0]
+    k1, k2 = np.array(a, np.uint64), np.array(b, np.uint64)
+    g1, g2 = np.zeros((n, 12), np.uint64), np.zeros((n, 24), np.uint64)
+    i1, i2 = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    sim.sim_gen_points(_p(k1), _p(k2), ctypes.c_size_t(n), _p(g1), _p(i1), _p(g2), _p(i2))
+    e1, ei1, e2, ei2 = util.oracle_points(coracle, seed, first, n)
+    assert np.array_equal(g1, e1) and np.array_equal(g2, e2) and not i1.any() and not i2.any()
+    for j in range(n):
+        assert coracle.group_op("g1", "on_curve", g1[j]) and coracle.group_op("g2", "on_curve", g2[j])
+    assert coracle.group_op("g2", "torsion_free", g2[0]) and coracle.group_op("g1", "torsion_free", g1[0])
+
+
+def test_pyref_splitmix_matches_util(pyref):
+    st, out = pyref.splitmix64(0x5EED)
+    a, _ = util.scalars_for(0x5EED, 0, 1)
+    assert out == a[0]

@@ -1,0 +1,301 @@
+"""CPU tests: pin the oracle (Python and C restatements) to the REFERENCE's own known-answer
+vectors (tests/golden/reference_kats.json, extracted from /root/reference/src tests) and to the
+published e(G1,G2) vector; cross-check the two restatements against each other."""
+import random
+
+import numpy as np
+import pytest
+
+import util
+from util import arr_fp, fp_arr, limbs_hex
+
+KATS = util.golden("reference_kats.json")
+VEC = util.golden("pairing_vectors.json")
+
+
+def fp6_from(rows):
+    v = [limbs_hex(r) for r in rows]
+    return ((v[0], v[1]), (v[2], v[3]), (v[4], v[5]))
+
+
+def fp12_from(rows):
+    return (fp6_from(rows[:6]), fp6_from(rows[6:]))
+
+
+# ---------------------------------------------------------------- reference KATs (Python oracle)
+
+def test_fp_sqrt_kat(pyref):            # src/fp.rs:577-588
+    k = KATS["fp_sqrt"]
+    assert "%096x" % pyref.fp_sqrt(k["input_u64"]) == k["sqrt_be_hex"]
+    assert pyref.fp_sqrt(k["non_residue_u64"]) is None
+
+
+def test_g1_double_kat(pyref):          # src/g1.rs:263-341
+    for case in KATS["g1_double"]["cases"]:
+        p = (limbs_hex(case["p"][0]), limbs_hex(case["p"][1]), False)
+        d = pyref.g1_double(p)
+        if case["asserted_by_reference"]:
+            assert (d[0], d[1]) == (limbs_hex(case["p2"][0]), limbs_hex(case["p2"][1]))
+    assert pyref.g1_is_valid(pyref.G1_GENERATOR)   # src/g1.rs:258
+
+
+def test_g2_double_and_torsion_kat(pyref):   # src/g2.rs:349-443
+    e = [limbs_hex(r) for r in KATS["g2_double_generator"]["p2"]]
+    d = pyref.g2_double(pyref.G2_GENERATOR)
+    assert d[0] == (e[0], e[1]) and d[1] == (e[2], e[3])
+    t = [limbs_hex(r) for r in KATS["g2_not_torsion_free"]["p"]]
+    pt = ((t[0], t[1]), (t[2], t[3]), False)
+    # the reference asserts only !is_torsion_free() for this point (src/g2.rs:441); read as canonical
+    # limbs it is not even on the curve (the literals are zkcrypto Montgomery-form limbs)
+    assert not pyref.g2_is_torsion_free(pt)
+    assert pyref.g2_is_torsion_free(pyref.G2_GENERATOR)
+    # src/g2.rs:277-346 : identity + identity, 4G + 2G == 6G
+    G = pyref.G2_GENERATOR
+    assert pyref.g2_add(pyref.G2_IDENTITY, pyref.G2_IDENTITY)[2]
+    assert pyref.g2_add(pyref.g2_mul(G, 4), pyref.g2_mul(G, 2))[:2] == pyref.g2_mul(G, 6)[:2]
+
+
+def test_fp6_fixed_operand_identities(pyref):   # src/fp6.rs:562-757
+    o = pyref
+    a, b, c = (fp6_from(KATS["fp6_abc"][k]) for k in "abc")
+    for x in (a, b, c):
+        assert o.fp6_square(x) == o.fp6_mul(x, x)
+    cc = o.fp6_square(c)
+    assert o.fp6_mul(o.fp6_add(a, b), cc) == o.fp6_add(o.fp6_mul(o.fp6_mul(c, c), a), o.fp6_mul(o.fp6_mul(c, c), b))
+    assert o.fp6_mul(o.fp6_invert(a), o.fp6_invert(b)) == o.fp6_invert(o.fp6_mul(a, b))
+    assert o.fp6_mul(o.fp6_invert(a), a) == o.FP6_ONE
+    for compat in (True, False):   # the reference only checks the ORDER of the map (:748-756)
+        x = a
+        for _ in range(6):
+            x = o.fp6_frobenius_map(x, ref_compat=compat)
+        assert x == a
+
+
+def test_fp12_fixed_operand_identities(pyref):  # src/fp12.rs:414-799
+    o = pyref
+    a, b, c = (fp12_from(KATS["fp12_abc"][k]) for k in "abc")
+    a = o.fp12_add(o.fp12_square(o.fp12_invert(o.fp12_square(a))), c)
+    b = o.fp12_add(o.fp12_square(o.fp12_invert(o.fp12_square(b))), a)
+    c = o.fp12_add(o.fp12_square(o.fp12_invert(o.fp12_square(c))), b)
+    for x in (a, b, c):
+        assert o.fp12_square(x) == o.fp12_mul(x, x)
+    cc = o.fp12_mul(c, c)
+    assert o.fp12_mul(o.fp12_add(a, b), o.fp12_square(c)) == o.fp12_add(o.fp12_mul(cc, a), o.fp12_mul(cc, b))
+    assert o.fp12_mul(o.fp12_invert(a), o.fp12_invert(b)) == o.fp12_invert(o.fp12_mul(a, b))
+    assert o.fp12_mul(o.fp12_invert(a), a) == o.FP12_ONE
+    for compat in (True, False):
+        assert a != o.fp12_frobenius_map(a, ref_compat=compat)
+        x = a
+        for _ in range(12):
+            x = o.fp12_frobenius_map(x, ref_compat=compat)
+        assert x == a
+
+
+def test_true_frobenius_is_pth_power_and_reference_is_not(pyref):
+    """the reference Fp6 constants are wrong; the oracle default is the true map."""
+    o = pyref
+    a = fp12_from(KATS["fp12_abc"]["a"])
+    assert o.fp12_frobenius_map(a) == o.fp12_pow_int(a, o.P)
+    assert o.fp12_frobenius_map(a, ref_compat=True) != o.fp12_pow_int(a, o.P)
+
+
+def test_g1_scalar_mul_quirk(pyref):
+    """src/g1.rs:130-153 drops bit 0 of the scalar (5*G == 4*G there); the oracle default is correct."""
+    G = pyref.G1_GENERATOR
+    assert pyref.g1_mul(G, 5, ref_compat=True) == pyref.g1_mul(G, 4)
+    assert pyref.g1_mul(G, 5) == pyref.g1_add(pyref.g1_mul(G, 4), G)
+    assert pyref.g1_mul(G, pyref.R_ORDER)[2] is True
+
+
+def test_algebraic_laws_like_reference(pyref):
+    """The reference's randomised law tests (src/fp.rs:501-614, fp2.rs:362-482, ...) on the oracle."""
+    o = pyref
+    rng = random.Random(5)
+    for _ in range(10):
+        a, b, c = (rng.randrange(o.P) for _ in range(3))
+        assert o.fp_mul(a, o.fp_add(b, c)) == o.fp_add(o.fp_mul(a, b), o.fp_mul(a, c))
+        assert o.fp_sub(a, b) == o.fp_add(a, o.fp_neg(b))
+        assert o.fp_div(a, a) == 1
+        assert o.fp_pow_vartime(a, [3, 0, 0, 0, 0, 0]) == o.fp_mul(o.fp_square(a), a)
+        x, y = (a, b), (c, a)
+        assert o.fp2_mul(x, y) == o.fp2_mul(y, x)
+        assert o.fp2_square(x) == o.fp2_mul(x, x)
+        assert o.fp2_mul(o.fp2_invert(x), x) == o.FP2_ONE
+    raw = [rng.getrandbits(64) for _ in range(12)]
+    # src/fp.rs:218-232 literally: (first six big-endian limbs) + (last six) * 2^384 -- a quirk of the
+    # canonical re-typing (zkcrypto multiplies by R^2 / R^3 in Montgomery form); only used by random()
+    hi = int.from_bytes(b"".join(w.to_bytes(8, "big") for w in raw[:6]), "big")
+    lo = int.from_bytes(b"".join(w.to_bytes(8, "big") for w in raw[6:]), "big")
+    assert o.fp_from_u768(raw) == (hi + lo * (1 << 384)) % o.P
+    assert o.fp_from_bytes(o.fp_to_bytes(o.P - 1)) == o.P - 1 and o.fp_from_bytes(o.fp_to_bytes(o.P)) is None
+
+
+# ---------------------------------------------------------------- pairing vectors (Python oracle)
+
+def test_generator_pairing_vector(pyref):
+    g = VEC["generators"]
+    ml = pyref.miller_loop(pyref.G1_GENERATOR, pyref.G2_GENERATOR)
+    assert pyref.fp12_sha256(ml) == "eceb6467936a62ed011881c3efceb3b9f05b6017afd264fa0caeebf4f8437115"
+    e = pyref.final_exponentiation(ml)
+    assert pyref.fp12_sha256(e) == "06fa588b89fdfb034dbc1c163ecb3dfac228f552b643c7294cc5f2c4dc170b84"
+    assert e == util.hex_fp12(g["pairing"]) and ml == util.hex_fp12(g["miller_loop"])
+    # first coefficient of the widely published BLS12-381 Gt generator
+    assert g["pairing"][0] == "1250ebd871fc0a92a7b2d83168d0d727272d441befa15c503dd8e90ce98db3e7b6d194f60839c508a84305aaca1789b6"
+
+
+def test_bilinearity_and_order(pyref):
+    o = pyref
+    e = util.hex_fp12(VEC["generators"]["pairing"])
+    assert e != o.FP12_ONE
+    assert o.fp12_pow_int(e, o.R_ORDER) == o.FP12_ONE
+    for case in VEC["pairings"][:4]:
+        a, b = int(case["a"], 16), int(case["b"], 16)
+        assert util.hex_fp12(case["pairing"]) == o.fp12_pow_int(e, a * b % o.R_ORDER)
+    inf_case = VEC["pairings"][-1]
+    assert util.hex_fp12(inf_case["pairing"]) == o.FP12_ONE
+
+
+def test_multi_miller_equals_product(pyref):
+    o = pyref
+    G1, G2 = o.G1_GENERATOR, o.G2_GENERATOR
+    pairs = [(o.g1_mul(G1, 3), o.g2_mul(G2, 5)), (o.g1_mul(G1, 7), G2), (G1, o.g2_mul(G2, 11))]
+    shared = o.multi_miller_loop(pairs)
+    prod = o.FP12_ONE
+    for p, q in pairs:
+        prod = o.fp12_mul(prod, o.miller_loop(p, q))
+    assert shared == prod
+    for chk in VEC["multi"]:
+        prs = [(util.hex_g1(x["g1"]), util.hex_g2(x["g2"])) for x in chk["pairs"]]
+        assert o.multi_miller_loop(prs) == util.hex_fp12(chk["multi_miller"])
+        assert (o.final_exponentiation(o.multi_miller_loop(prs)) == o.FP12_ONE) == chk["is_one"]
+
+
+def test_work_model_counts(pyref):
+    """The Fp-mul counts the roofline uses: 6,916 Miller + 9,101 final exp
+    (+3 because the oracle's pow_vartime also squares the leading one three times)."""
+    o = pyref
+    o.KARATSUBA = True
+    try:
+        o.reset_counter()
+        ml = o.miller_loop(o.G1_GENERATOR, o.G2_GENERATOR)
+        m = o.FP_MULS
+        o.reset_counter()
+        o.final_exponentiation(ml)
+        f = o.FP_MULS
+    finally:
+        o.KARATSUBA = False
+    assert m == 6916 and f == 9101 + 3
+
+
+# ---------------------------------------------------------------- C oracle vs Python oracle / KATs
+
+def test_c_oracle_reference_kats(coracle, pyref):
+    for case in KATS["g1_double"]["cases"]:
+        if not case["asserted_by_reference"]:
+            continue
+        p = fp_arr([limbs_hex(case["p"][0]), limbs_hex(case["p"][1])])
+        out, inf = coracle.group_op("g1", "double", p)
+        assert arr_fp(out) == [limbs_hex(case["p2"][0]), limbs_hex(case["p2"][1])] and inf == 0
+    out, _ = coracle.group_op("g2", "double", util.g2_to_arr(pyref.G2_GENERATOR))
+    assert arr_fp(out) == [limbs_hex(r) for r in KATS["g2_double_generator"]["p2"]]
+    t = fp_arr([limbs_hex(r) for r in KATS["g2_not_torsion_free"]["p"]])
+    assert not coracle.group_op("g2", "torsion_free", t)
+    assert coracle.group_op("g2", "on_curve", t) == pyref.g2_is_on_curve(((limbs_hex(KATS["g2_not_torsion_free"]["p"][0]), limbs_hex(KATS["g2_not_torsion_free"]["p"][1])),
+                                                                         (limbs_hex(KATS["g2_not_torsion_free"]["p"][2]), limbs_hex(KATS["g2_not_torsion_free"]["p"][3])), False))
+    assert coracle.group_op("g2", "torsion_free", util.g2_to_arr(pyref.G2_GENERATOR))
+    assert coracle.group_op("g1", "torsion_free", util.g1_to_arr(pyref.G1_GENERATOR))
+    k = KATS["fp_sqrt"]
+    out, ok = coracle.tower_op("fp_sqrt", fp_arr([k["input_u64"], k["non_residue_u64"]]), want_ok=True)
+    assert "%096x" % arr_fp(out[0])[0] == k["sqrt_be_hex"] and list(ok) == [1, 0]
+
+
+PY_OPS = {
+    "fp_add": lambda o, a, b: o.fp_add(a, b), "fp_sub": lambda o, a, b: o.fp_sub(a, b), "fp_neg": lambda o, a, b: o.fp_neg(a),
+    "fp_mul": lambda o, a, b: o.fp_mul(a, b), "fp_sqr": lambda o, a, b: o.fp_square(a), "fp_inv": lambda o, a, b: o.fp_invert(a) or 0,
+}
+
+
+@pytest.mark.parametrize("name", ["fp12_mul", "fp12_sqr", "fp12_inv", "fp12_frob", "fp12_conj", "fp12_mul_by_014", "fp12_cyc_sqr",
+                                  "fp6_mul", "fp6_sqr", "fp6_inv", "fp6_frob", "fp6_mul_by_1", "fp6_mul_by_01", "fp2_mul", "fp2_sqr", "fp2_inv"])
+def test_c_oracle_matches_python(coracle, pyref, name):
+    o = pyref
+    from zkvm_pairings_b200 import op_widths
+    na, nb, nr = op_widths(name)
+    n = 6
+    a = util.random_fp_matrix(n, na, seed=11)
+    b = util.random_fp_matrix(n, nb or na, seed=12)
+    got = coracle.tower_op(name, a, b)
+
+    def pack(vals, w):
+        if w == 2:
+            return (vals[0], vals[1])
+        if w == 6:
+            return ((vals[0], vals[1]), (vals[2], vals[3]), (vals[4], vals[5]))
+        return o.fp12_unflatten(vals)
+
+    def flat(x, w):
+        if w == 2:
+            return list(x)
+        if w == 6:
+            return [c for t in x for c in t]
+        return o.fp12_flatten(x)
+
+    fn = {
+        "fp12_mul": lambda x, y: o.fp12_mul(x, y), "fp12_sqr": lambda x, y: o.fp12_square(x),
+        "fp12_inv": lambda x, y: o.fp12_invert(x) or o.FP12_ZERO, "fp12_frob": lambda x, y: o.fp12_frobenius_map(x),
+        "fp12_conj": lambda x, y: o.fp12_conjugate(x), "fp12_cyc_sqr": lambda x, y: o.cyclotomic_square(x),
+        "fp12_mul_by_014": lambda x, y: o.fp12_mul_by_014(x, (y[0], y[1]), (y[2], y[3]), (y[4], y[5])),
+        "fp6_mul": lambda x, y: o.fp6_mul(x, y), "fp6_sqr": lambda x, y: o.fp6_square(x),
+        "fp6_inv": lambda x, y: o.fp6_invert(x) or o.FP6_ZERO, "fp6_frob": lambda x, y: o.fp6_frobenius_map(x),
+        "fp6_mul_by_1": lambda x, y: o.fp6_mul_by_1(x, (y[0], y[1])),
+        "fp6_mul_by_01": lambda x, y: o.fp6_mul_by_01(x, (y[0], y[1]), (y[2], y[3])),
+        "fp2_mul": lambda x, y: o.fp2_mul(x, y), "fp2_sqr": lambda x, y: o.fp2_square(x), "fp2_inv": lambda x, y: o.fp2_invert(x) or o.FP2_ZERO,
+    }[name]
+    for i in range(n):
+        x = pack(arr_fp(a[i]), na)
+        yv = arr_fp(b[i])
+        y = pack(yv, nb) if nb in (2, 6, 12) and name not in ("fp6_mul_by_1", "fp6_mul_by_01", "fp12_mul_by_014") else yv
+        assert flat(fn(x, y), nr) == arr_fp(got[i]), (name, i)
+
+
+def test_c_oracle_pairing_vectors(coracle, pyref):
+    cases = VEC["pairings"]
+    g1 = np.stack([util.g1_to_arr(util.hex_g1(c["g1"])) for c in cases])
+    g2 = np.stack([util.g2_to_arr(util.hex_g2(c["g2"])) for c in cases])
+    i1 = np.array([c["g1"]["inf"] for c in cases], dtype=np.uint8)
+    i2 = np.array([c["g2"]["inf"] for c in cases], dtype=np.uint8)
+    ml = coracle.miller_loop_batch(g1, i1, g2, i2)
+    gt = coracle.pairing_batch(g1, i1, g2, i2)
+    for k, c in enumerate(cases):
+        assert util.arr_to_fp12(ml[k]) == util.hex_fp12(c["miller_loop"])
+        assert util.arr_to_fp12(gt[k]) == util.hex_fp12(c["pairing"])
+    assert np.array_equal(coracle.final_exp_batch(ml), gt)
+    for chk in VEC["multi"]:
+        a1 = np.stack([util.g1_to_arr(util.hex_g1(x["g1"])) for x in chk["pairs"]])
+        a2 = np.stack([util.g2_to_arr(util.hex_g2(x["g2"])) for x in chk["pairs"]])
+        out, one = coracle.multi_pairing_batch(a1, None, a2, None, k=4)
+        assert util.arr_to_fp12(out[0]) == util.hex_fp12(chk["gt"]) and bool(one[0]) == chk["is_one"]
+        mm = coracle.multi_miller_batch(a1, None, a2, None, k=4)
+        assert util.arr_to_fp12(mm[0]) == util.hex_fp12(chk["multi_miller"])
+        prod, gt2 = coracle.miller_product(a1, None, a2, None)
+        assert np.array_equal(prod, mm[0]) and np.array_equal(gt2, out[0])
+
+
+def test_c_oracle_rejects_noncanonical(coracle, pyref):
+    g1 = util.g1_to_arr(pyref.G1_GENERATOR)[None].copy()
+    g2 = util.g2_to_arr(pyref.G2_GENERATOR)[None]
+    g1[0, :6] = fp_arr([pyref.P])   # x = p, not canonical
+    with pytest.raises(ValueError):
+        coracle.pairing_batch(g1, None, g2, None)
+
+
+def test_c_oracle_scalar_mul_matches_python(coracle, pyref):
+    ks = [1, 2, 3, 0xdeadbeefcafebabe, pyref.R_ORDER - 1, pyref.R_ORDER]
+    g1, i1 = coracle.g1_mul_batch(util.scalar_matrix(ks))
+    g2, i2 = coracle.g2_mul_batch(util.scalar_matrix(ks))
+    for j, k in enumerate(ks):
+        p, q = pyref.g1_mul(pyref.G1_GENERATOR, k), pyref.g2_mul(pyref.G2_GENERATOR, k)
+        assert bool(i1[j]) == p[2] and bool(i2[j]) == q[2]
+        if not p[2]:
+            assert arr_fp(g1[j]) == [p[0], p[1]]
+            assert arr_fp(g2[j]) == [q[0][0], q[0][1], q[1][0], q[1][1]]

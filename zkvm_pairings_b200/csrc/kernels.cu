@@ -1,0 +1,762 @@
+// libzkpair.so: CUDA kernels (sm_100a) + the C ABI declared in include/zkpair.h.
+//
+// One thread owns one pairing check (k pairs -> shared-accumulator Miller loop -> final
+// exponentiation); a warp therefore runs 32 independent checks in lock-step (the control flow is
+// data independent), and the integer-multiply pipe is kept busy by the carry-chain Montgomery
+// product in fp.cuh.  Independent checks shard in contiguous slices over the context's devices;
+// the only cross-device traffic is the 576-byte Fp12 partial of zkp_multi_miller_product.
+//
+// There is deliberately no CPU implementation in this library: with no CUDA device every entry
+// point fails with ZKP_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/zkpair.h"
+#include "ops.cuh"
+
+#ifndef ZKP_TPB
+#define ZKP_TPB 128           // threads per block of the pairing kernels
+#endif
+#ifndef ZKP_MIN_BLOCKS
+#define ZKP_MIN_BLOCKS 2      // resident blocks per SM the register allocator must allow
+#endif
+#ifndef ZKP_CHUNK
+#define ZKP_CHUNK (1u << 17)  // checks per host<->device pipeline chunk
+#endif
+
+using namespace zkp;
+
+// ================================================================== kernels
+
+__global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS)
+k_tower_op(int op, const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, uint64_t *__restrict__ out,
+           uint8_t *__restrict__ status, uint32_t *err, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int na, nb, nr;
+    tower_op_shape(op, na, nb, nr);
+    uint8_t s = tower_op_one(op, a + (size_t)6 * na * i, nb ? b + (size_t)6 * nb * i : nullptr, out + (size_t)6 * nr * i);
+    if (status) status[i] = s;
+    if ((s & 1) && err) atomicOr(err, 1u);
+}
+
+// mode: bit0 Miller loop, bit1 final exponentiation.  One thread per check of k (<= K) pairs.
+template <int K>
+__global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS)
+k_pairing(int mode, const uint64_t *__restrict__ g1, const uint8_t *__restrict__ g1inf,
+          const uint64_t *__restrict__ g2, const uint8_t *__restrict__ g2inf, int k,
+          const uint64_t *__restrict__ in12, uint64_t *__restrict__ out, uint8_t *__restrict__ is_one,
+          uint32_t *err, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    size_t e = i * (size_t)k;
+    uint8_t s = pairing_one<K>(mode, g1 ? g1 + 12 * e : nullptr, g1inf ? g1inf + e : nullptr,
+                               g2 ? g2 + 24 * e : nullptr, g2inf ? g2inf + e : nullptr, k,
+                               in12 ? in12 + 72 * i : nullptr, out + 72 * i, is_one ? is_one + i : nullptr);
+    if (s && err) atomicOr(err, 1u);
+}
+
+// out[t] = in[t] * in[t+m] * in[t+2m] * ...   (t < m <= n), canonical limbs in and out
+__global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS)
+k_fp12_product(const uint64_t *__restrict__ in, size_t n, uint64_t *__restrict__ out, size_t m, uint32_t *err) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    bool bad = false;
+    Fp12 acc, x;
+    load_fp12(acc, in + 72 * t, bad);
+    for (size_t j = t + m; j < n; j += m) {
+        load_fp12(x, in + 72 * j, bad);
+        fp12_mul(acc, acc, x);
+    }
+    store_fp12(out + 72 * t, acc);
+    if (bad && err) atomicOr(err, 1u);
+}
+
+__global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS)
+k_gen_points(uint64_t seed, uint64_t first, size_t n, uint64_t *__restrict__ g1, uint8_t *__restrict__ g1inf,
+             uint64_t *__restrict__ g2, uint8_t *__restrict__ g2inf) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t a = splitmix64_at(seed, 2 * (first + i));
+    uint64_t b = splitmix64_at(seed, 2 * (first + i) + 1);
+    if (a == 0) a = 1;
+    if (b == 0) b = 1;
+    gen_g1_one(a, g1 + 12 * i, g1inf + i);
+    gen_g2_one(b, g2 + 24 * i, g2inf + i);
+}
+
+// Integer-multiply roofline probe.  KIND 0: 8 independent IMAD.WIDE.U32 accumulate chains per
+// thread; KIND 1: 8 independent 32-bit IMAD chains; KIND 2: the carry-chained wide MACs exactly as
+// the Montgomery rows issue them (two 6-MAC chains per step).
+template <int KIND>
+__global__ void __launch_bounds__(256) k_imad_peak(uint32_t *sink, int iters) {
+    uint32_t x = threadIdx.x * 2654435761u + 12345u, y = blockIdx.x * 40503u + 977u;
+    if (KIND == 0) {
+        uint64_t acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) acc[c] = x + c;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(x), "r"(y));
+        }
+        uint64_t s = 0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) s ^= acc[c];
+        if (s == 0x123456789abcdefull) sink[0] = (uint32_t)s;
+    } else if (KIND == 1) {
+        uint32_t acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) acc[c] = x + c;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[c]) : "r"(x), "r"(y));
+        }
+        uint32_t s = 0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) s ^= acc[c];
+        if (s == 0x12345678u) sink[0] = s;
+    } else {
+        uint32_t ev[12], od[12], a[12];
+#pragma unroll
+        for (int c = 0; c < 12; c++) { ev[c] = x + c; od[c] = y + c; a[c] = x * (c + 3) + y; }
+        for (int it = 0; it < iters; it++) {
+            chain_mad<0>(ev, a, y);
+            chain_mad<1>(od, a, x);
+        }
+        uint32_t s = 0;
+#pragma unroll
+        for (int c = 0; c < 12; c++) s ^= ev[c] ^ od[c];
+        if (s == 0x12345678u) sink[0] = s;
+    }
+}
+
+// ================================================================== host side
+
+static thread_local std::string g_err;
+static int32_t fail(int32_t code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ZKP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+enum { B_G1 = 0, B_G1INF, B_G2, B_G2INF, B_IN, B_OUT, B_FLAG, B_NBUF };
+
+struct DevState {
+    int id = 0;
+    int sms = 0;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    uint32_t *d_err = nullptr;
+    DevBuf buf[2][B_NBUF];     // double-buffered pipeline scratch
+    DevBuf scratch, partial;   // product reduction
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timers;
+    double timed_ms = 0;
+    uint64_t timed_launches = 0;
+};
+
+struct zkp_ctx {
+    std::vector<DevState> devs;
+    std::mutex mu;
+    std::atomic<uint64_t> launches{0};
+    bool timing = false;
+};
+
+static inline unsigned grid_for(size_t n) { return (unsigned)((n + ZKP_TPB - 1) / ZKP_TPB); }
+
+static int pair_capacity(int k) { return k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : 8; }
+
+static cudaError_t launch_pairing(zkp_ctx *ctx, DevState &d, int mode, const uint64_t *g1, const uint8_t *g1inf,
+                                  const uint64_t *g2, const uint8_t *g2inf, size_t n, int k, const uint64_t *in12,
+                                  uint64_t *out, uint8_t *is_one, uint32_t *err, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->timing) {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+    }
+    dim3 g(grid_for(n)), b(ZKP_TPB);
+    switch (pair_capacity(k)) {
+        case 1: k_pairing<1><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n); break;
+        case 2: k_pairing<2><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n); break;
+        case 4: k_pairing<4><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n); break;
+        default: k_pairing<8><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n); break;
+    }
+    ctx->launches++;
+    if (ctx->timing) {
+        cudaEventRecord(e1, st);
+        d.timers.emplace_back(e0, e1);
+    }
+    return cudaGetLastError();
+}
+
+// product of n canonical Fp12 at d_in -> d_out (1 element).  scratch: zkp_product_scratch_elems(n)
+static const size_t PROD_M1 = 8192, PROD_M2 = 64;
+extern "C" size_t zkp_product_scratch_elems(size_t n) {
+    (void)n;
+    return PROD_M1 + PROD_M2;
+}
+static cudaError_t launch_product(zkp_ctx *ctx, const uint64_t *d_in, size_t n, uint64_t *d_scratch, uint64_t *d_out,
+                                  uint32_t *err, cudaStream_t st) {
+    const uint64_t *cur = d_in;
+    size_t cnt = n;
+    uint64_t *s1 = d_scratch, *s2 = d_scratch + 72 * PROD_M1;
+    if (cnt > PROD_M1) {
+        k_fp12_product<<<grid_for(PROD_M1), ZKP_TPB, 0, st>>>(cur, cnt, s1, PROD_M1, err);
+        ctx->launches++;
+        cur = s1;
+        cnt = PROD_M1;
+    }
+    if (cnt > PROD_M2) {
+        k_fp12_product<<<grid_for(PROD_M2), ZKP_TPB, 0, st>>>(cur, cnt, s2, PROD_M2, err);
+        ctx->launches++;
+        cur = s2;
+        cnt = PROD_M2;
+    }
+    k_fp12_product<<<1, ZKP_TPB, 0, st>>>(cur, cnt, d_out, 1, err);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+extern "C" {
+
+const char *zkp_last_error(void) { return g_err.c_str(); }
+
+const char *zkp_version(void) {
+    static char buf[160];
+    snprintf(buf, sizeof buf, "zkpair 0.1 (sm_100a, tpb=%d, min_blocks=%d, chunk=%u)", ZKP_TPB, ZKP_MIN_BLOCKS, (unsigned)ZKP_CHUNK);
+    return buf;
+}
+
+int32_t zkp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int32_t zkp_ctx_create(const int *devices, int n_devices, zkp_ctx **out) {
+    if (!out) return fail(ZKP_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    int avail = zkp_device_count();
+    if (avail <= 0) return fail(ZKP_ERR_NO_DEVICE, "no CUDA device available (libzkpair has no CPU path)");
+    std::vector<int> ids;
+    if (!devices || n_devices <= 0) {
+        for (int i = 0; i < avail; i++) ids.push_back(i);
+    } else {
+        for (int i = 0; i < n_devices; i++) {
+            if (devices[i] < 0 || devices[i] >= avail) return fail(ZKP_ERR_INVALID_ARG, "device index out of range");
+            ids.push_back(devices[i]);
+        }
+    }
+    zkp_ctx *c = new zkp_ctx();
+    c->devs.resize(ids.size());
+    for (size_t i = 0; i < ids.size(); i++) {
+        DevState &d = c->devs[i];
+        d.id = ids[i];
+        cudaError_t e = cudaSetDevice(d.id);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream[0], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream[1], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc(&d.d_err, sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMemset(d.d_err, 0, sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, d.id);
+        if (e != cudaSuccess) {
+            std::string msg = std::string("device init failed: ") + cudaGetErrorString(e);
+            zkp_ctx_destroy(c);
+            return fail(ZKP_ERR_CUDA, msg);
+        }
+    }
+    *out = c;
+    return ZKP_OK;
+}
+
+void zkp_ctx_destroy(zkp_ctx *ctx) {
+    if (!ctx) return;
+    for (DevState &d : ctx->devs) {
+        cudaSetDevice(d.id);
+        for (auto &t : d.timers) {
+            cudaEventDestroy(t.first);
+            cudaEventDestroy(t.second);
+        }
+        for (int s = 0; s < 2; s++) {
+            for (int b = 0; b < B_NBUF; b++) d.buf[s][b].release();
+            if (d.stream[s]) cudaStreamDestroy(d.stream[s]);
+        }
+        d.scratch.release();
+        d.partial.release();
+        if (d.d_err) cudaFree(d.d_err);
+    }
+    delete ctx;
+}
+
+int32_t zkp_ctx_num_devices(const zkp_ctx *ctx) { return ctx ? (int32_t)ctx->devs.size() : 0; }
+uint64_t zkp_launch_count(const zkp_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int32_t zkp_set_kernel_timing(zkp_ctx *ctx, int32_t enabled) {
+    if (!ctx) return fail(ZKP_ERR_INVALID_ARG, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->timing = enabled != 0;
+    return ZKP_OK;
+}
+
+int32_t zkp_last_kernel_ms(zkp_ctx *ctx, int32_t dev, double *total_ms, uint64_t *launches) {
+    if (!ctx || dev < 0 || dev >= (int)ctx->devs.size()) return fail(ZKP_ERR_INVALID_ARG, "bad ctx/dev");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState &d = ctx->devs[dev];
+    CU(cudaSetDevice(d.id));
+    for (auto &t : d.timers) {
+        CU(cudaEventSynchronize(t.second));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, t.first, t.second));
+        d.timed_ms += ms;
+        d.timed_launches++;
+        cudaEventDestroy(t.first);
+        cudaEventDestroy(t.second);
+    }
+    d.timers.clear();
+    if (total_ms) *total_ms = d.timed_ms;
+    if (launches) *launches = d.timed_launches;
+    d.timed_ms = 0;
+    d.timed_launches = 0;
+    return ZKP_OK;
+}
+
+// ------------------------------------------------------------------ device-resident entry points
+
+static int32_t check_dev(zkp_ctx *ctx, int32_t dev) {
+    if (!ctx) return fail(ZKP_ERR_INVALID_ARG, "ctx is NULL");
+    if (dev < 0 || dev >= (int)ctx->devs.size()) return fail(ZKP_ERR_INVALID_ARG, "device index out of range");
+    return ZKP_OK;
+}
+
+int32_t zkp_pairing_dev(zkp_ctx *ctx, int32_t dev, int32_t mode, const uint64_t *d_g1_xy, const uint8_t *d_g1_inf,
+                        const uint64_t *d_g2_xy, const uint8_t *d_g2_inf, size_t n_checks, int32_t pairs_per_check,
+                        const uint64_t *d_in_fp12, uint64_t *d_out, uint8_t *d_is_one, uint32_t *d_err, void *stream) {
+    int32_t rc = check_dev(ctx, dev);
+    if (rc) return rc;
+    if (mode < 1 || mode > 3 || !d_out) return fail(ZKP_ERR_INVALID_ARG, "bad mode / NULL output");
+    if ((mode & 1) && (!d_g1_xy || !d_g2_xy || pairs_per_check < 1)) return fail(ZKP_ERR_INVALID_ARG, "NULL point buffers");
+    if (!(mode & 1) && !d_in_fp12) return fail(ZKP_ERR_INVALID_ARG, "NULL Fp12 input");
+    if (pairs_per_check > ZKP_MAX_PAIRS_PER_CHECK) return fail(ZKP_ERR_TOO_MANY_PAIRS, "pairs_per_check > 8");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState &d = ctx->devs[dev];
+    CU(cudaSetDevice(d.id));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
+    CU(launch_pairing(ctx, d, mode, d_g1_xy, d_g1_inf, d_g2_xy, d_g2_inf, n_checks, (mode & 1) ? pairs_per_check : 1,
+                      d_in_fp12, d_out, d_is_one, d_err, st));
+    return ZKP_OK;
+}
+
+int32_t zkp_tower_op_dev(zkp_ctx *ctx, int32_t dev, int32_t op, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out,
+                         uint8_t *d_status, uint32_t *d_err, size_t n, void *stream) {
+    int32_t rc = check_dev(ctx, dev);
+    if (rc) return rc;
+    int na, nb, nr;
+    tower_op_shape(op, na, nb, nr);
+    if (!d_a || !d_out || (nb && !d_b)) return fail(ZKP_ERR_INVALID_ARG, "NULL operand");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState &d = ctx->devs[dev];
+    CU(cudaSetDevice(d.id));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
+    if (n) {
+        k_tower_op<<<grid_for(n), ZKP_TPB, 0, st>>>(op, d_a, d_b, d_out, d_status, d_err, n);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    return ZKP_OK;
+}
+
+int32_t zkp_fp12_product_dev(zkp_ctx *ctx, int32_t dev, const uint64_t *d_in, size_t n, uint64_t *d_scratch,
+                             uint64_t *d_out, uint32_t *d_err, void *stream) {
+    int32_t rc = check_dev(ctx, dev);
+    if (rc) return rc;
+    if (!d_in || !d_out || !d_scratch || n == 0) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer or n == 0");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState &d = ctx->devs[dev];
+    CU(cudaSetDevice(d.id));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
+    CU(launch_product(ctx, d_in, n, d_scratch, d_out, d_err, st));
+    return ZKP_OK;
+}
+
+int32_t zkp_gen_points_dev(zkp_ctx *ctx, int32_t dev, uint64_t seed, uint64_t first, size_t n, uint64_t *d_g1_xy,
+                           uint8_t *d_g1_inf, uint64_t *d_g2_xy, uint8_t *d_g2_inf, void *stream) {
+    int32_t rc = check_dev(ctx, dev);
+    if (rc) return rc;
+    if (!d_g1_xy || !d_g1_inf || !d_g2_xy || !d_g2_inf) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState &d = ctx->devs[dev];
+    CU(cudaSetDevice(d.id));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
+    if (n) {
+        k_gen_points<<<grid_for(n), ZKP_TPB, 0, st>>>(seed, first, n, d_g1_xy, d_g1_inf, d_g2_xy, d_g2_inf);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    return ZKP_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer entry points
+
+// Split [0,n) into one contiguous slice per device.
+static void slice_of(size_t n, size_t ndev, size_t d, size_t &lo, size_t &hi) {
+    lo = n * d / ndev;
+    hi = n * (d + 1) / ndev;
+}
+
+struct HostJob {
+    int mode = 0;   // 1 miller, 2 final exp, 3 pairing ; 16 = tower op ; 32 = gen points
+    const uint64_t *g1 = nullptr, *g2 = nullptr, *in12 = nullptr, *a = nullptr, *b = nullptr;
+    const uint8_t *g1inf = nullptr, *g2inf = nullptr;
+    uint64_t *out = nullptr, *og1 = nullptr, *og2 = nullptr;
+    uint8_t *flags = nullptr, *og1inf = nullptr, *og2inf = nullptr;
+    int k = 1, op = 0;
+    uint64_t seed = 0, first = 0;
+};
+
+// Runs elements [lo,hi) of a job on one device with a two-stage copy/compute pipeline.
+static int32_t run_slice(zkp_ctx *ctx, DevState &d, const HostJob &j, size_t lo, size_t hi, std::string &msg) {
+#define CUS(call)                                                                     \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            msg = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+            return ZKP_ERR_CUDA;                                                      \
+        }                                                                             \
+    } while (0)
+    CUS(cudaSetDevice(d.id));
+    CUS(cudaMemsetAsync(d.d_err, 0, sizeof(uint32_t), d.stream[0]));
+    CUS(cudaStreamSynchronize(d.stream[0]));
+    int na = 0, nb = 0, nr = 0;
+    if (j.mode == 16) tower_op_shape(j.op, na, nb, nr);
+    size_t chunk = ZKP_CHUNK;
+    int s = 0;
+    for (size_t c0 = lo; c0 < hi; c0 += chunk, s ^= 1) {
+        size_t cn = hi - c0 < chunk ? hi - c0 : chunk;
+        cudaStream_t st = d.stream[s];
+        DevBuf *B = d.buf[s];
+        CUS(cudaStreamSynchronize(st));   // this buffer set's previous chunk is fully drained
+        if (j.mode == 16) {
+            CUS(B[B_IN].ensure(cn * na * 48));
+            CUS(B[B_OUT].ensure(cn * nr * 48));
+            CUS(B[B_FLAG].ensure(cn));
+            CUS(cudaMemcpyAsync(B[B_IN].p, j.a + c0 * na * 6, cn * na * 48, cudaMemcpyHostToDevice, st));
+            if (nb) {
+                CUS(B[B_G2].ensure(cn * nb * 48));
+                CUS(cudaMemcpyAsync(B[B_G2].p, j.b + c0 * nb * 6, cn * nb * 48, cudaMemcpyHostToDevice, st));
+            }
+            k_tower_op<<<grid_for(cn), ZKP_TPB, 0, st>>>(j.op, (const uint64_t *)B[B_IN].p, nb ? (const uint64_t *)B[B_G2].p : nullptr,
+                                                        (uint64_t *)B[B_OUT].p, (uint8_t *)B[B_FLAG].p, d.d_err, cn);
+            ctx->launches++;
+            CUS(cudaGetLastError());
+            CUS(cudaMemcpyAsync(j.out + c0 * nr * 6, B[B_OUT].p, cn * nr * 48, cudaMemcpyDeviceToHost, st));
+            if (j.flags) CUS(cudaMemcpyAsync(j.flags + c0, B[B_FLAG].p, cn, cudaMemcpyDeviceToHost, st));
+        } else if (j.mode == 32) {
+            CUS(B[B_G1].ensure(cn * 96));
+            CUS(B[B_G2].ensure(cn * 192));
+            CUS(B[B_G1INF].ensure(cn));
+            CUS(B[B_G2INF].ensure(cn));
+            k_gen_points<<<grid_for(cn), ZKP_TPB, 0, st>>>(j.seed, j.first + c0, cn, (uint64_t *)B[B_G1].p, (uint8_t *)B[B_G1INF].p,
+                                                          (uint64_t *)B[B_G2].p, (uint8_t *)B[B_G2INF].p);
+            ctx->launches++;
+            CUS(cudaGetLastError());
+            CUS(cudaMemcpyAsync(j.og1 + c0 * 12, B[B_G1].p, cn * 96, cudaMemcpyDeviceToHost, st));
+            CUS(cudaMemcpyAsync(j.og2 + c0 * 24, B[B_G2].p, cn * 192, cudaMemcpyDeviceToHost, st));
+            CUS(cudaMemcpyAsync(j.og1inf + c0, B[B_G1INF].p, cn, cudaMemcpyDeviceToHost, st));
+            CUS(cudaMemcpyAsync(j.og2inf + c0, B[B_G2INF].p, cn, cudaMemcpyDeviceToHost, st));
+        } else {
+            size_t np = cn * (size_t)j.k, p0 = c0 * (size_t)j.k;
+            const uint8_t *di1 = nullptr, *di2 = nullptr;
+            if (j.mode & 1) {
+                CUS(B[B_G1].ensure(np * 96));
+                CUS(B[B_G2].ensure(np * 192));
+                CUS(cudaMemcpyAsync(B[B_G1].p, j.g1 + p0 * 12, np * 96, cudaMemcpyHostToDevice, st));
+                CUS(cudaMemcpyAsync(B[B_G2].p, j.g2 + p0 * 24, np * 192, cudaMemcpyHostToDevice, st));
+                if (j.g1inf) {
+                    CUS(B[B_G1INF].ensure(np));
+                    CUS(cudaMemcpyAsync(B[B_G1INF].p, j.g1inf + p0, np, cudaMemcpyHostToDevice, st));
+                    di1 = (const uint8_t *)B[B_G1INF].p;
+                }
+                if (j.g2inf) {
+                    CUS(B[B_G2INF].ensure(np));
+                    CUS(cudaMemcpyAsync(B[B_G2INF].p, j.g2inf + p0, np, cudaMemcpyHostToDevice, st));
+                    di2 = (const uint8_t *)B[B_G2INF].p;
+                }
+            } else {
+                CUS(B[B_IN].ensure(cn * 576));
+                CUS(cudaMemcpyAsync(B[B_IN].p, j.in12 + c0 * 72, cn * 576, cudaMemcpyHostToDevice, st));
+            }
+            CUS(B[B_OUT].ensure(cn * 576));
+            if (j.flags) CUS(B[B_FLAG].ensure(cn));
+            CUS(launch_pairing(ctx, d, j.mode, (const uint64_t *)B[B_G1].p, di1, (const uint64_t *)B[B_G2].p, di2, cn, j.k,
+                               (const uint64_t *)B[B_IN].p, (uint64_t *)B[B_OUT].p, j.flags ? (uint8_t *)B[B_FLAG].p : nullptr,
+                               d.d_err, st));
+            CUS(cudaMemcpyAsync(j.out + c0 * 72, B[B_OUT].p, cn * 576, cudaMemcpyDeviceToHost, st));
+            if (j.flags) CUS(cudaMemcpyAsync(j.flags + c0, B[B_FLAG].p, cn, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CUS(cudaStreamSynchronize(d.stream[0]));
+    CUS(cudaStreamSynchronize(d.stream[1]));
+    uint32_t herr = 0;
+    CUS(cudaMemcpy(&herr, d.d_err, sizeof herr, cudaMemcpyDeviceToHost));
+    if (herr & 1) {
+        msg = "input limb vector >= p (non-canonical field element)";
+        return ZKP_ERR_NONCANONICAL;
+    }
+    return ZKP_OK;
+#undef CUS
+}
+
+static int32_t run_host_job(zkp_ctx *ctx, const HostJob &j, size_t n) {
+    if (!ctx) return fail(ZKP_ERR_INVALID_ARG, "ctx is NULL");
+    if (n == 0) return ZKP_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    size_t nd = ctx->devs.size();
+    std::vector<int32_t> rcs(nd, ZKP_OK);
+    std::vector<std::string> msgs(nd);
+    if (nd == 1 || n < 2 * nd) {
+        rcs[0] = run_slice(ctx, ctx->devs[0], j, 0, n, msgs[0]);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t d = 0; d < nd; d++) {
+            size_t lo, hi;
+            slice_of(n, nd, d, lo, hi);
+            th.emplace_back([&, d, lo, hi]() { rcs[d] = run_slice(ctx, ctx->devs[d], j, lo, hi, msgs[d]); });
+        }
+        for (auto &t : th) t.join();
+    }
+    for (size_t d = 0; d < nd; d++)
+        if (rcs[d] != ZKP_OK) return fail(rcs[d], msgs[d]);
+    return ZKP_OK;
+}
+
+int32_t zkp_tower_op_batch(zkp_ctx *ctx, int32_t op, const uint64_t *a, const uint64_t *b, uint64_t *out, uint8_t *status, size_t n) {
+    int na, nb, nr;
+    tower_op_shape(op, na, nb, nr);
+    bool known = (op >= 0 && op <= OP_FP_INV) || (op >= OP_FP2_ADD && op <= OP_FP2_CONJ) || (op >= OP_FP6_ADD && op <= OP_FP6_MUL_BY_01) ||
+                 (op >= OP_FP12_ADD && op <= OP_FP12_FROB3);
+    if (!known) return fail(ZKP_ERR_INVALID_ARG, "unknown tower op");
+    if (n && (!a || !out || (nb && !b))) return fail(ZKP_ERR_INVALID_ARG, "NULL operand");
+    HostJob j;
+    j.mode = 16; j.op = op; j.a = a; j.b = b; j.out = out; j.flags = status;
+    return run_host_job(ctx, j, n);
+}
+int32_t zkp_fp_mul_batch(zkp_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
+    return zkp_tower_op_batch(ctx, OP_FP_MUL, a, b, out, nullptr, n);
+}
+int32_t zkp_fp12_mul_batch(zkp_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
+    return zkp_tower_op_batch(ctx, OP_FP12_MUL, a, b, out, nullptr, n);
+}
+int32_t zkp_fp12_mul_by_014_batch(zkp_ctx *ctx, const uint64_t *f, const uint64_t *c, uint64_t *out, size_t n) {
+    return zkp_tower_op_batch(ctx, OP_FP12_MUL_BY_014, f, c, out, nullptr, n);
+}
+
+static int32_t pairs_job(zkp_ctx *ctx, int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
+                         size_t n, int32_t k, uint64_t *out, uint8_t *flags) {
+    if (k < 1) return fail(ZKP_ERR_INVALID_ARG, "pairs_per_check < 1");
+    if (k > ZKP_MAX_PAIRS_PER_CHECK) return fail(ZKP_ERR_TOO_MANY_PAIRS, "pairs_per_check > 8 (use zkp_multi_miller_product)");
+    if (n && (!g1 || !g2 || !out)) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
+    HostJob j;
+    j.mode = mode; j.g1 = g1; j.g1inf = g1inf; j.g2 = g2; j.g2inf = g2inf; j.k = k; j.out = out; j.flags = flags;
+    return run_host_job(ctx, j, n);
+}
+int32_t zkp_miller_loop_batch(zkp_ctx *ctx, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf, size_t n, uint64_t *out) {
+    return pairs_job(ctx, 1, g1, g1inf, g2, g2inf, n, 1, out, nullptr);
+}
+int32_t zkp_pairing_batch(zkp_ctx *ctx, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf, size_t n, uint64_t *out) {
+    return pairs_job(ctx, 3, g1, g1inf, g2, g2inf, n, 1, out, nullptr);
+}
+int32_t zkp_multi_miller_loop_batch(zkp_ctx *ctx, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
+                                    size_t n_checks, int32_t k, uint64_t *out) {
+    return pairs_job(ctx, 1, g1, g1inf, g2, g2inf, n_checks, k, out, nullptr);
+}
+int32_t zkp_multi_pairing_batch(zkp_ctx *ctx, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
+                                size_t n_checks, int32_t k, uint64_t *out, uint8_t *is_one) {
+    return pairs_job(ctx, 3, g1, g1inf, g2, g2inf, n_checks, k, out, is_one);
+}
+int32_t zkp_final_exp_batch(zkp_ctx *ctx, const uint64_t *in, size_t n, uint64_t *out) {
+    if (n && (!in || !out)) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
+    HostJob j;
+    j.mode = 2; j.in12 = in; j.out = out;
+    return run_host_job(ctx, j, n);
+}
+int32_t zkp_gen_points(zkp_ctx *ctx, uint64_t seed, uint64_t first, size_t n, uint64_t *g1, uint8_t *g1inf, uint64_t *g2, uint8_t *g2inf) {
+    if (n && (!g1 || !g1inf || !g2 || !g2inf)) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
+    HostJob j;
+    j.mode = 32; j.seed = seed; j.first = first; j.og1 = g1; j.og1inf = g1inf; j.og2 = g2; j.og2inf = g2inf;
+    return run_host_job(ctx, j, n);
+}
+
+// One large product: per-device Miller loops over a contiguous slice -> per-device Fp12 partial ->
+// gather the 576-byte partials on the first device -> multiply -> ONE final exponentiation.
+int32_t zkp_multi_miller_product(zkp_ctx *ctx, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
+                                 size_t n, uint64_t *out_miller_product, uint64_t *out_gt) {
+    if (!ctx) return fail(ZKP_ERR_INVALID_ARG, "ctx is NULL");
+    if (!g1 || !g2 || n == 0) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer or n == 0");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    size_t nd = ctx->devs.size();
+    if (n < nd) nd = 1;
+    std::vector<int32_t> rcs(nd, ZKP_OK);
+    std::vector<std::string> msgs(nd);
+    // each device: chunks of Miller loops, each chunk folded to one Fp12 appended to d.partial
+    auto worker = [&](size_t di) {
+        DevState &d = ctx->devs[di];
+        std::string &msg = msgs[di];
+        int32_t &rc = rcs[di];
+#define CUW(call)                                                                     \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            msg = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+            rc = ZKP_ERR_CUDA;                                                        \
+            return;                                                                   \
+        }                                                                             \
+    } while (0)
+        size_t lo, hi;
+        slice_of(n, nd, di, lo, hi);
+        CUW(cudaSetDevice(d.id));
+        cudaStream_t st = d.stream[0];
+        CUW(cudaMemsetAsync(d.d_err, 0, sizeof(uint32_t), st));
+        size_t chunk = ZKP_CHUNK, nchunks = (hi - lo + chunk - 1) / chunk;
+        CUW(d.partial.ensure((nchunks + 1) * 576));
+        CUW(d.scratch.ensure(zkp_product_scratch_elems(chunk) * 576));
+        DevBuf *B = d.buf[0];
+        size_t ci = 0;
+        for (size_t c0 = lo; c0 < hi; c0 += chunk, ci++) {
+            size_t cn = hi - c0 < chunk ? hi - c0 : chunk;
+            CUW(B[B_G1].ensure(cn * 96));
+            CUW(B[B_G2].ensure(cn * 192));
+            CUW(B[B_OUT].ensure(cn * 576));
+            CUW(cudaMemcpyAsync(B[B_G1].p, g1 + c0 * 12, cn * 96, cudaMemcpyHostToDevice, st));
+            CUW(cudaMemcpyAsync(B[B_G2].p, g2 + c0 * 24, cn * 192, cudaMemcpyHostToDevice, st));
+            const uint8_t *di1 = nullptr, *di2 = nullptr;
+            if (g1inf) {
+                CUW(B[B_G1INF].ensure(cn));
+                CUW(cudaMemcpyAsync(B[B_G1INF].p, g1inf + c0, cn, cudaMemcpyHostToDevice, st));
+                di1 = (const uint8_t *)B[B_G1INF].p;
+            }
+            if (g2inf) {
+                CUW(B[B_G2INF].ensure(cn));
+                CUW(cudaMemcpyAsync(B[B_G2INF].p, g2inf + c0, cn, cudaMemcpyHostToDevice, st));
+                di2 = (const uint8_t *)B[B_G2INF].p;
+            }
+            CUW(launch_pairing(ctx, d, 1, (const uint64_t *)B[B_G1].p, di1, (const uint64_t *)B[B_G2].p, di2, cn, 1, nullptr,
+                               (uint64_t *)B[B_OUT].p, nullptr, d.d_err, st));
+            CUW(launch_product(ctx, (const uint64_t *)B[B_OUT].p, cn, (uint64_t *)d.scratch.p, (uint64_t *)d.partial.p + 72 * ci, d.d_err, st));
+        }
+        // fold this device's chunk partials into slot `nchunks`
+        CUW(launch_product(ctx, (const uint64_t *)d.partial.p, nchunks, (uint64_t *)d.scratch.p, (uint64_t *)d.partial.p + 72 * nchunks, d.d_err, st));
+        CUW(cudaStreamSynchronize(st));
+        uint32_t herr = 0;
+        CUW(cudaMemcpy(&herr, d.d_err, sizeof herr, cudaMemcpyDeviceToHost));
+        if (herr & 1) {
+            msg = "input limb vector >= p (non-canonical field element)";
+            rc = ZKP_ERR_NONCANONICAL;
+        }
+#undef CUW
+    };
+    if (nd == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t di = 0; di < nd; di++) th.emplace_back(worker, di);
+        for (auto &t : th) t.join();
+    }
+    for (size_t di = 0; di < nd; di++)
+        if (rcs[di] != ZKP_OK) return fail(rcs[di], msgs[di]);
+    // gather: one 576-byte partial per device -> first device (peer copy over NVLink when available)
+    DevState &d0 = ctx->devs[0];
+    CU(cudaSetDevice(d0.id));
+    DevBuf &G = d0.buf[1][B_IN];
+    CU(G.ensure((nd + 2) * 576));
+    for (size_t di = 0; di < nd; di++) {
+        DevState &d = ctx->devs[di];
+        size_t lo, hi;
+        slice_of(n, nd, di, lo, hi);
+        size_t nchunks = (hi - lo + ZKP_CHUNK - 1) / ZKP_CHUNK;
+        const uint64_t *src = (const uint64_t *)d.partial.p + 72 * nchunks;
+        if (d.id == d0.id)
+            CU(cudaMemcpyAsync((uint64_t *)G.p + 72 * di, src, 576, cudaMemcpyDeviceToDevice, d0.stream[0]));
+        else
+            CU(cudaMemcpyPeerAsync((uint64_t *)G.p + 72 * di, d0.id, src, d.id, 576, d0.stream[0]));
+    }
+    uint64_t *prod = (uint64_t *)G.p + 72 * nd, *gt = (uint64_t *)G.p + 72 * (nd + 1);
+    CU(d0.scratch.ensure(zkp_product_scratch_elems(nd) * 576));
+    CU(launch_product(ctx, (const uint64_t *)G.p, nd, (uint64_t *)d0.scratch.p, prod, d0.d_err, d0.stream[0]));
+    if (out_gt) CU(launch_pairing(ctx, d0, 2, nullptr, nullptr, nullptr, nullptr, 1, 1, prod, gt, nullptr, d0.d_err, d0.stream[0]));
+    if (out_miller_product) CU(cudaMemcpyAsync(out_miller_product, prod, 576, cudaMemcpyDeviceToHost, d0.stream[0]));
+    if (out_gt) CU(cudaMemcpyAsync(out_gt, gt, 576, cudaMemcpyDeviceToHost, d0.stream[0]));
+    CU(cudaStreamSynchronize(d0.stream[0]));
+    return ZKP_OK;
+}
+
+// ------------------------------------------------------------------ measurement
+
+int32_t zkp_imad_peak(zkp_ctx *ctx, int32_t dev, int32_t kind, double *macs_per_second) {
+    int32_t rc = check_dev(ctx, dev);
+    if (rc) return rc;
+    if (!macs_per_second || kind < 0 || kind > 2) return fail(ZKP_ERR_INVALID_ARG, "bad kind / NULL out");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState &d = ctx->devs[dev];
+    CU(cudaSetDevice(d.id));
+    cudaStream_t st = d.stream[0];
+    uint32_t *sink = d.d_err;
+    const int iters = 1 << 13, blocks = d.sms * 8, threads = 256;
+    const double per_thread = (double)iters * (kind == 2 ? 12.0 : 8.0);
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CU(cudaEventRecord(e0, st));
+        if (kind == 0) k_imad_peak<0><<<blocks, threads, 0, st>>>(sink + 0, iters);
+        else if (kind == 1) k_imad_peak<1><<<blocks, threads, 0, st>>>(sink + 0, iters);
+        else k_imad_peak<2><<<blocks, threads, 0, st>>>(sink + 0, iters);
+        ctx->launches++;
+        CU(cudaEventRecord(e1, st));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CU(cudaMemsetAsync(d.d_err, 0, sizeof(uint32_t), st));
+    CU(cudaStreamSynchronize(st));
+    *macs_per_second = per_thread * blocks * threads / (best * 1e-3);
+    return ZKP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+// Boundary marshalling + per-element operation bodies shared by the CUDA kernels (kernels.cu) and
+// the CPU dev-simulation used by the not-gpu tests (tests/host_sim/sim.cpp).
+//
+// Boundary layout (host and device buffers): canonical little-endian u64 limbs, array-of-structs,
+// exactly `Fp.0` of the reference (/root/reference/src/fp.rs:24): Fp = 6 u64, Fp2 = (c0,c1),
+// Fp6 = (c0,c1,c2), Fp12 = (c0,c1) = 72 u64; G1 = x|y, G2 = x.c0|x.c1|y.c0|y.c1.
+#pragma once
+#include "pairing.cuh"
+
+namespace zkp {
+
+// op codes of the element-wise tower entry point (zkp_tower_op_batch)
+enum TowerOp {
+    OP_FP_ADD = 0, OP_FP_SUB, OP_FP_NEG, OP_FP_MUL, OP_FP_SQR, OP_FP_INV,
+    OP_FP2_ADD = 16, OP_FP2_SUB, OP_FP2_NEG, OP_FP2_MUL, OP_FP2_SQR, OP_FP2_INV, OP_FP2_MUL_NR, OP_FP2_CONJ,
+    OP_FP6_ADD = 32, OP_FP6_SUB, OP_FP6_NEG, OP_FP6_MUL, OP_FP6_SQR, OP_FP6_INV, OP_FP6_MUL_NR, OP_FP6_FROB, OP_FP6_MUL_BY_1, OP_FP6_MUL_BY_01,
+    OP_FP12_ADD = 48, OP_FP12_SUB, OP_FP12_NEG, OP_FP12_MUL, OP_FP12_SQR, OP_FP12_INV, OP_FP12_CONJ, OP_FP12_FROB, OP_FP12_MUL_BY_014, OP_FP12_CYC_SQR, OP_FP12_CYC_EXP,
+    OP_FP12_FROB2 = 59, OP_FP12_FROB3 = 60
+};
+
+// number of Fp in operand a / operand b / result for an op (0 = operand unused)
+ZKP_HOSTDEV void tower_op_shape(int op, int &na, int &nb, int &nr) {
+    int w = op < 16 ? 1 : op < 32 ? 2 : op < 48 ? 6 : 12;
+    na = w; nr = w; nb = 0;
+    switch (op) {
+        case OP_FP_ADD: case OP_FP_SUB: case OP_FP_MUL:
+        case OP_FP2_ADD: case OP_FP2_SUB: case OP_FP2_MUL:
+        case OP_FP6_ADD: case OP_FP6_SUB: case OP_FP6_MUL:
+        case OP_FP12_ADD: case OP_FP12_SUB: case OP_FP12_MUL: nb = w; break;
+        case OP_FP6_MUL_BY_1: nb = 2; break;
+        case OP_FP6_MUL_BY_01: nb = 4; break;
+        case OP_FP12_MUL_BY_014: nb = 6; break;
+        default: break;
+    }
+}
+
+// canonical u64 limbs -> Montgomery Fp.  Sets bad when the value is >= p.
+ZKP_HD Fp load_fp(const uint64_t *src, bool &bad) {
+    Fp a;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        uint64_t w = src[i];
+        a.l[2 * i] = (uint32_t)w;
+        a.l[2 * i + 1] = (uint32_t)(w >> 32);
+    }
+    bad = bad | !fp_is_canonical(a);
+    return fp_to_mont(a);
+}
+ZKP_HD void store_fp(uint64_t *dst, const Fp &m) {
+    Fp a = fp_from_mont(m);
+#pragma unroll
+    for (int i = 0; i < 6; i++) dst[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
+}
+ZKP_HD void load_fps(Fp *dst, const uint64_t *src, int n, bool &bad) {
+    for (int i = 0; i < n; i++) dst[i] = load_fp(src + 6 * i, bad);
+}
+ZKP_HD void store_fps(uint64_t *dst, const Fp *src, int n) {
+    for (int i = 0; i < n; i++) store_fp(dst + 6 * i, src[i]);
+}
+
+// One element of a batched tower op.  a/b/out point at this element's limbs.  Returns a status
+// byte: bit0 = non-canonical input, bit1 = inverse of zero requested (result is zero).
+ZKP_HD uint8_t tower_op_one(int op, const uint64_t *a, const uint64_t *b, uint64_t *out) {
+    int na, nb, nr;
+    tower_op_shape(op, na, nb, nr);
+    bool bad = false, noinv = false;
+    // operands live in one Fp12-sized union-like buffer set (kept simple: arrays of Fp)
+    Fp12 A, B, R;
+    Fp *pa = &A.c0.c0.c0, *pb = &B.c0.c0.c0, *pr = &R.c0.c0.c0;
+    load_fps(pa, a, na, bad);
+    if (nb) load_fps(pb, b, nb, bad);
+    const Fp2 *a2 = &A.c0.c0, *b2 = &B.c0.c0;
+    Fp2 *r2 = &R.c0.c0;
+    switch (op) {
+        case OP_FP_ADD: pr[0] = fp_add(pa[0], pb[0]); break;
+        case OP_FP_SUB: pr[0] = fp_sub(pa[0], pb[0]); break;
+        case OP_FP_NEG: pr[0] = fp_neg(pa[0]); break;
+        case OP_FP_MUL: pr[0] = fmul(pa[0], pb[0]); break;
+        case OP_FP_SQR: pr[0] = fsqr(pa[0]); break;
+        case OP_FP_INV: noinv = fp_is_zero(pa[0]); pr[0] = fp_inv(pa[0]); break;
+        case OP_FP2_ADD: r2[0] = fp2_add(a2[0], b2[0]); break;
+        case OP_FP2_SUB: r2[0] = fp2_sub(a2[0], b2[0]); break;
+        case OP_FP2_NEG: r2[0] = fp2_neg(a2[0]); break;
+        case OP_FP2_MUL: r2[0] = fp2_mul(a2[0], b2[0]); break;
+        case OP_FP2_SQR: r2[0] = fp2_sqr(a2[0]); break;
+        case OP_FP2_INV: noinv = fp2_is_zero(a2[0]); r2[0] = fp2_inv(a2[0]); break;
+        case OP_FP2_MUL_NR: r2[0] = fp2_mul_nr(a2[0]); break;
+        case OP_FP2_CONJ: r2[0] = fp2_conj(a2[0]); break;
+        case OP_FP6_ADD: fp6_add(R.c0, A.c0, B.c0); break;
+        case OP_FP6_SUB: fp6_sub(R.c0, A.c0, B.c0); break;
+        case OP_FP6_NEG: fp6_neg(R.c0, A.c0); break;
+        case OP_FP6_MUL: fp6_mul(R.c0, A.c0, B.c0); break;
+        case OP_FP6_SQR: fp6_sqr(R.c0, A.c0); break;
+        case OP_FP6_INV: noinv = fp2_is_zero(A.c0.c0) & fp2_is_zero(A.c0.c1) & fp2_is_zero(A.c0.c2); fp6_inv(R.c0, A.c0); break;
+        case OP_FP6_MUL_NR: fp6_mul_nr(R.c0, A.c0); break;
+        case OP_FP6_FROB: {   // Fp6 embedded as c0 of an Fp12: frobenius acts coefficient-wise
+            fp6_set_zero(A.c1);
+            fp12_frobenius(R, A, 1);
+        } break;
+        case OP_FP6_MUL_BY_1: fp6_mul_by_1(R.c0, A.c0, b2[0]); break;
+        case OP_FP6_MUL_BY_01: fp6_mul_by_01(R.c0, A.c0, b2[0], b2[1]); break;
+        case OP_FP12_ADD: fp6_add(R.c0, A.c0, B.c0); fp6_add(R.c1, A.c1, B.c1); break;
+        case OP_FP12_SUB: fp6_sub(R.c0, A.c0, B.c0); fp6_sub(R.c1, A.c1, B.c1); break;
+        case OP_FP12_NEG: fp6_neg(R.c0, A.c0); fp6_neg(R.c1, A.c1); break;
+        case OP_FP12_MUL: fp12_mul(R, A, B); break;
+        case OP_FP12_SQR: fp12_sqr(R, A); break;
+        case OP_FP12_INV: {
+            bool z = true;
+            for (int i = 0; i < 12; i++) z = z & fp_is_zero(pa[i]);
+            noinv = z;
+            fp12_inv(R, A);
+        } break;
+        case OP_FP12_CONJ: fp12_conj(R, A); break;
+        case OP_FP12_FROB: fp12_frobenius(R, A, 1); break;
+        case OP_FP12_FROB2: fp12_frobenius(R, A, 2); break;
+        case OP_FP12_FROB3: fp12_frobenius(R, A, 3); break;
+        case OP_FP12_MUL_BY_014: R = A; fp12_mul_by_014(R, b2[0], b2[1], b2[2]); break;
+        case OP_FP12_CYC_SQR: fp12_cyclotomic_sqr(R, A); break;
+        case OP_FP12_CYC_EXP: cyclotomic_exp(R, A); break;
+        default: bad = true; nr = 0; break;
+    }
+    store_fps(out, pr, nr);
+    return (uint8_t)((bad ? 1 : 0) | (noinv ? 2 : 0));
+}
+
+ZKP_HD void load_g1(G1A &p, const uint64_t *xy, bool &bad) { p.x = load_fp(xy, bad); p.y = load_fp(xy + 6, bad); }
+ZKP_HD void load_g2(G2A &q, const uint64_t *xy, bool &bad) {
+    q.x.c0 = load_fp(xy, bad); q.x.c1 = load_fp(xy + 6, bad);
+    q.y.c0 = load_fp(xy + 12, bad); q.y.c1 = load_fp(xy + 18, bad);
+}
+ZKP_HD void store_fp12(uint64_t *dst, const Fp12 &f) { store_fps(dst, &f.c0.c0.c0, 12); }
+ZKP_HD void load_fp12(Fp12 &f, const uint64_t *src, bool &bad) { load_fps(&f.c0.c0.c0, src, 12, bad); }
+
+// mode bits for pairing_one
+enum { ZKP_DO_MILLER = 1, ZKP_DO_FINAL_EXP = 2 };
+
+// One "check": k pairs -> shared-accumulator Miller loop (-> final exponentiation).  g1/g2/inf
+// point at this check's first pair.  Returns status bit0 = non-canonical input.
+// is_one (optional) receives 1 when the result equals Fp12::one().  K = compile-time capacity
+// (k <= K) so the per-thread scratch is sized for the common k = 1 case.
+template <int K>
+ZKP_HD uint8_t pairing_one(int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
+                           int k, const uint64_t *in12, uint64_t *out, uint8_t *is_one) {
+    bool bad = false;
+    Fp12 f;
+    if (mode & ZKP_DO_MILLER) {
+        G1A ps[K];
+        G2A qs[K];
+        G2P rs[K];
+        bool skip[K];
+        for (int j = 0; j < k; j++) {
+            load_g1(ps[j], g1 + 12 * j, bad);
+            load_g2(qs[j], g2 + 24 * j, bad);
+            skip[j] = (g1inf && g1inf[j]) | (g2inf && g2inf[j]);
+        }
+        miller_loop(f, ps, qs, skip, rs, k);
+    } else {
+        load_fp12(f, in12, bad);
+    }
+    if (mode & ZKP_DO_FINAL_EXP) final_exponentiation(f, f);
+    store_fp12(out, f);
+    if (is_one) *is_one = fp12_is_one(f) ? 1 : 0;
+    return bad ? 1 : 0;
+}
+
+// SplitMix64 output number idx+1 of the stream seeded with `seed` (random access)
+ZKP_HD uint64_t splitmix64_at(uint64_t seed, uint64_t idx) {
+    uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// [k]G for the G1 / G2 generators, k = 64-bit scalar (synthetic input generation, untimed)
+ZKP_HD void gen_g1_one(uint64_t k, uint64_t *xy, uint8_t *inf) {
+    Fp gx, gy, ax, ay;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { gx.l[i] = ZKP_G1_GEN[i]; gy.l[i] = ZKP_G1_GEN[12 + i]; }
+    *inf = scalar_mul_affine<OpsFp>(ax, ay, gx, gy, &k, 64) ? 1 : 0;
+    store_fp(xy, ax);
+    store_fp(xy + 6, ay);
+}
+ZKP_HD void gen_g2_one(uint64_t k, uint64_t *xy, uint8_t *inf) {
+    Fp2 gx, gy, ax, ay;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        gx.c0.l[i] = ZKP_G2_GEN[i]; gx.c1.l[i] = ZKP_G2_GEN[12 + i];
+        gy.c0.l[i] = ZKP_G2_GEN[24 + i]; gy.c1.l[i] = ZKP_G2_GEN[36 + i];
+    }
+    *inf = scalar_mul_affine<OpsFp2>(ax, ay, gx, gy, &k, 64) ? 1 : 0;
+    store_fp(xy, ax.c0); store_fp(xy + 6, ax.c1);
+    store_fp(xy + 12, ay.c0); store_fp(xy + 18, ay.c1);
+}
+
+}  // namespace zkp
