@@ -181,8 +181,13 @@ def run_ours(args):
 
     n = 1 << args.log2_batch
     eng = z.PairingEngine([local])
-    st = torch.cuda.current_stream().cuda_stream
     dev = torch.device("cuda", local)
+    # a non-default torch stream: its handle is non-zero, so the C ABI launches on it (NULL would
+    # mean "the context's own stream") and torch.cuda.Event timing sees the kernels
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    st = tstream.cuda_stream
+    assert st != 0
 
     # ---- synthetic inputs, generated on the device (valid subgroup points), untimed
     g1 = torch.empty((n, 12), dtype=torch.int64, device=dev)

@@ -1,0 +1,40 @@
+#!/usr/bin/env python3
+"""Profiling target: ONE launch of each pairing-path kernel on 2^LOG2 device-resident pairs
+(after generating the inputs on the device).  Usage: python tools/prof_pairing.py [LOG2] [mode...]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import zkvm_pairings_b200 as z
+
+log2 = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+modes = [int(m) for m in sys.argv[2:]] or [3]
+n = 1 << log2
+eng = z.PairingEngine([0])
+dev = torch.device("cuda", 0)
+s = torch.cuda.Stream(device=dev)
+torch.cuda.set_stream(s)
+g1 = torch.empty((n, 12), dtype=torch.int64, device=dev)
+g2 = torch.empty((n, 24), dtype=torch.int64, device=dev)
+i1 = torch.empty(n, dtype=torch.uint8, device=dev)
+i2 = torch.empty(n, dtype=torch.uint8, device=dev)
+out = torch.empty((n, 72), dtype=torch.int64, device=dev)
+ml = torch.empty((n, 72), dtype=torch.int64, device=dev)
+eng.gen_points_dev(7, 0, n, g1, i1, g2, i2, stream=s.cuda_stream)
+torch.cuda.synchronize()
+for m in modes:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    if m == 2:
+        eng.pairing_dev(1, ml, g1=g1, g2=g2, stream=s.cuda_stream)
+        e0.record()
+        eng.pairing_dev(2, out, in_fp12=ml, stream=s.cuda_stream)
+    else:
+        eng.pairing_dev(m, out, g1=g1, g2=g2, stream=s.cuda_stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print("mode %d: n=%d  %.3f ms  %.0f /s" % (m, n, ms, n / ms * 1e3))
+eng.close()
