@@ -41,3 +41,9 @@ void sim_gen_points(const uint64_t *k1, const uint64_t *k2, size_t n, uint64_t *
     }
 }
 }
+
+#ifdef ZKP_TRACK_BOUNDS
+extern "C" void sim_max_bounds(double *out) {
+    out[0] = zkp::g_max_lb; out[1] = zkp::g_max_tb; out[2] = zkp::g_max_vb; out[3] = zkp::g_max_col;
+}
+#endif

@@ -1,21 +1,29 @@
-// Fp: BLS12-381 base field on sm_100a -- 12 x 32-bit limbs, Montgomery form (R = 2^384).
+// Fp: BLS12-381 base field on sm_100a -- 14 signed limbs of 28 bits, Montgomery form R = 2^392.
 //
 // Replaces the reference's host Fp arithmetic (BigUint mul/add followed by "% p",
 // /root/reference/src/fp.rs:351-368, :415-434) and its zkVM precompile calls
 // (bls12381_sys_bigint / syscall_bls12381_fp_mulmod, src/fp.rs:126,376,443).  Values cross the
-// boundary as canonical little-endian limbs (src/fp.rs:24); inside the kernels they are in
-// Montgomery form.
+// boundary as canonical little-endian limbs (src/fp.rs:24) and are converted at load/store.
 //
-// The multiplier is a CIOS Montgomery product written as carry chains of 32x32->64 wide
-// multiply-accumulates (PTX mad.lo.cc/madc.hi.cc pairs, which ptxas fuses into one
-// IMAD.WIDE.U32 with carry-in/out predicates).  Partial products are kept in two interleaved
-// accumulators ("even" = 64-bit aligned columns, "odd" = columns offset by 32 bits) so every
-// wide MAC lands on a register pair and the two chains of a row are independent (ILP 2).
-// 12 rows x (12 a*b + 12 m*p) + 12 (m = t0 * n0') = 300 wide MACs per product.
+// Why 14 x 28 bits and not 12 x 32 (the v0 design): on B200 a plain IMAD.WIDE issues at the full
+// fmaheavy rate (measured 18.2 T/s) but the carry-chained IMAD.WIDE.U32.X that saturated 32-bit
+// limbs need issues at HALF of it (9.1 T/s; profiles/r1a_v0_saturated_cios_ncu_summary.txt).
+// With 28-bit limbs every 32x32->64 product has 8 spare bits, so whole columns of partial products
+// accumulate in 64-bit registers with NO carries: a Montgomery product is 14*14 (a*b) + 14*14
+// (m*p) + 14 (m = t*n0') = 420 full-rate IMADs with 14-way instruction-level parallelism, against
+// 300 half-rate ones before.  Additions and subtractions become 14 independent 32-bit adds (no
+// carry chain, no conditional subtraction): limbs are SIGNED and values are kept lazily reduced.
 //
-// The same header compiles as plain C++ (ZKP_HOST_SIM) with the carry flag emulated, so the
-// limb-level algorithm is exercised by the CPU test-suite.  That build is a DEV SIMULATION of the
-// device code for tests only; it is never linked into libzkpair.so.
+// Representation invariants (checked statically by the bound tracker, see ZKP_TRACK_BOUNDS):
+//   * value  v = sum l[i] * 2^(28 i), congruent to (x * 2^392) mod p, |v| < 2^11 * p;
+//   * "normalized": l[0..12] in [0, 2^28), l[13] small and signed (it carries the sign of v);
+//   * add/sub/neg are limb-wise and only grow the limb bound; fp_wnorm() brings l[0..12] back to
+//     [-16, 2^28 + 16] in one parallel round;
+//   * fp_mul needs  14 * max|a.l| * max|b.l| + 2^60 < 2^63  and returns a normalized value in
+//     (ab/R, ab/R + p), i.e. within (-0.1p, 1.1p) for operands below 16p.
+//
+// The header is plain C++ (no PTX), so the identical code is exercised on the CPU by the dev
+// simulation tests/host_sim/sim.cpp (never linked into libzkpair.so).
 #pragma once
 #include <stdint.h>
 
@@ -36,228 +44,274 @@
 
 #include "consts.cuh"
 
-namespace zkp {
-
-struct Fp {
-    uint32_t l[12];
-};
-
-// ------------------------------------------------------------------ carry-chain primitives
-#ifdef ZKP_DEVICE_BUILD
-ZKP_HD uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-ZKP_HD uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-ZKP_HD uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-ZKP_HD uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-ZKP_HD uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-ZKP_HD uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-ZKP_HD uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
-ZKP_HD uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
-ZKP_HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
-ZKP_HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
-#else
-// host emulation of the PTX condition-code register (one flag per thread)
-static thread_local uint32_t ZKP_CF = 0;
-ZKP_HD uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b; ZKP_CF = (uint32_t)(s >> 32); return (uint32_t)s; }
-ZKP_HD uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b + ZKP_CF; ZKP_CF = (uint32_t)(s >> 32); return (uint32_t)s; }
-ZKP_HD uint32_t addc(uint32_t a, uint32_t b) { return a + b + ZKP_CF; }
-ZKP_HD uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t d = (uint64_t)a - b; ZKP_CF = (uint32_t)(d >> 63); return (uint32_t)d; }
-ZKP_HD uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t d = (uint64_t)a - b - ZKP_CF; ZKP_CF = (uint32_t)(d >> 63); return (uint32_t)d; }
-ZKP_HD uint32_t subc(uint32_t a, uint32_t b) { return a - b - ZKP_CF; }
-ZKP_HD uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (uint64_t)(uint32_t)(a * b) + c; ZKP_CF = (uint32_t)(s >> 32); return (uint32_t)s; }
-ZKP_HD uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (uint64_t)(uint32_t)(a * b) + c + ZKP_CF; ZKP_CF = (uint32_t)(s >> 32); return (uint32_t)s; }
-ZKP_HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (((uint64_t)a * b) >> 32) + c + ZKP_CF; ZKP_CF = (uint32_t)(s >> 32); return (uint32_t)s; }
-ZKP_HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)(((uint64_t)a * b) >> 32) + c + ZKP_CF; }
+#ifdef ZKP_TRACK_BOUNDS
+#include <cstdio>
+#include <cstdlib>
+#include <execinfo.h>
 #endif
 
-// ------------------------------------------------------------------ basic ops
+namespace zkp {
 
+#define ZKP_NL 14
+#define ZKP_M28 0x0fffffff
+
+struct Fp {
+    int32_t l[ZKP_NL];
+#ifdef ZKP_TRACK_BOUNDS
+    // worst-case bounds carried along in the CPU dev simulation only: |l[0..12]| <= lb,
+    // |l[13]| <= tb, |value| <= vb * p.  They depend on the formula DAG, not on the data.
+    double lb, tb, vb;
+#endif
+};
+
+#ifdef ZKP_TRACK_BOUNDS
+#define ZKP_TOP_PER_P 106514.0          /* ceil(p / 2^364) */
+#define ZKP_R_OVER_P 2520.0             /* floor(2^392 / p) */
+static double g_max_lb = 0, g_max_tb = 0, g_max_vb = 0, g_max_col = 0;
+static inline void zkp_bound_fail(const char *what, double v) {
+    fprintf(stderr, "ZKP bound violation: %s (%.4g = 2^%.2f)\n", what, v, __builtin_log2(v));
+    void *bt[32];
+    int n = backtrace(bt, 32);
+    backtrace_symbols_fd(bt, n, 2);
+    abort();
+}
+static inline void zkp_set_bounds(Fp &r, double lb, double tb, double vb) {
+    r.lb = lb; r.tb = tb; r.vb = vb;
+    if (lb > g_max_lb) g_max_lb = lb;
+    if (tb > g_max_tb) g_max_tb = tb;
+    if (vb > g_max_vb) g_max_vb = vb;
+    if (lb >= 2147483000.0) zkp_bound_fail("limb magnitude reaches 2^31", lb);
+    if (tb >= 2147483000.0) zkp_bound_fail("top limb magnitude reaches 2^31", tb);
+}
+#define ZKP_SETB(r, lb, tb, vb) zkp_set_bounds(r, lb, tb, vb)
+#else
+#define ZKP_SETB(r, lb, tb, vb)
+#endif
+
+// ------------------------------------------------------------------ constants / trivial ops
+ZKP_HD Fp fp_const(const int32_t *k) {   // a normalized constant (Montgomery form), value < p
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < ZKP_NL; i++) r.l[i] = k[i];
+    ZKP_SETB(r, 268435456.0, ZKP_TOP_PER_P, 1.0);
+    return r;
+}
 ZKP_HD Fp fp_zero() {
     Fp r;
 #pragma unroll
-    for (int i = 0; i < 12; i++) r.l[i] = 0;
+    for (int i = 0; i < ZKP_NL; i++) r.l[i] = 0;
+    ZKP_SETB(r, 0.0, 0.0, 0.0);
     return r;
 }
-ZKP_HD Fp fp_one() {   // Montgomery form of 1; canonical one is [1,0,..] (src/fp.rs:154-156)
-    Fp r;
-#pragma unroll
-    for (int i = 0; i < 12; i++) r.l[i] = ZKP_ONE[i];
-    return r;
-}
-ZKP_HD bool fp_is_zero(const Fp &a) {
-    uint32_t t = 0;
-#pragma unroll
-    for (int i = 0; i < 12; i++) t |= a.l[i];
-    return t == 0;
-}
-ZKP_HD bool fp_eq(const Fp &a, const Fp &b) {   // raw-limb equality, like src/fp.rs:53-58
-    uint32_t t = 0;
-#pragma unroll
-    for (int i = 0; i < 12; i++) t |= a.l[i] ^ b.l[i];
-    return t == 0;
-}
+ZKP_HD Fp fp_one() { return fp_const(ZKP_ONE); }   // Montgomery one; canonical one is [1,0,..] (src/fp.rs:154-156)
 
-// r = a - k, returns borrow mask (0xffffffff when a < k); k = 12 constant limbs
-ZKP_HD uint32_t sub_limbs(Fp &r, const Fp &a, const uint32_t *k) {
-    r.l[0] = sub_cc(a.l[0], k[0]);
-#pragma unroll
-    for (int i = 1; i < 12; i++) r.l[i] = subc_cc(a.l[i], k[i]);
-    return subc(0, 0);
-}
-// a in [0, 2p) -> [0, p)
-ZKP_HD Fp fp_reduce_once(const Fp &a) {
-    Fp t;
-    uint32_t borrow = sub_limbs(t, a, ZKP_P);
+// (a + b), lazily: no carry, no reduction   -- value-equal mod p to src/fp.rs:351-368
+ZKP_HD Fp fp_add(const Fp &a, const Fp &b) {
     Fp r;
 #pragma unroll
-    for (int i = 0; i < 12; i++) r.l[i] = borrow ? a.l[i] : t.l[i];
+    for (int i = 0; i < ZKP_NL; i++) r.l[i] = a.l[i] + b.l[i];
+    ZKP_SETB(r, a.lb + b.lb, a.tb + b.tb, a.vb + b.vb);
     return r;
 }
-// a + b without reduction (caller guarantees the sum stays below 2^384)
-ZKP_HD Fp fp_add_nr(const Fp &a, const Fp &b) {
-    Fp r;
-    r.l[0] = add_cc(a.l[0], b.l[0]);
-#pragma unroll
-    for (int i = 1; i < 11; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
-    r.l[11] = addc(a.l[11], b.l[11]);
-    return r;
-}
-// (a + b) mod p for a, b in [0,p)   -- src/fp.rs:351-368
-ZKP_HD Fp fp_add(const Fp &a, const Fp &b) { return fp_reduce_once(fp_add_nr(a, b)); }
-// (a - b) mod p for a, b in [0,p)   -- src/fp.rs:407-411
+// (a - b), lazily (limbs are signed)        -- src/fp.rs:407-411
 ZKP_HD Fp fp_sub(const Fp &a, const Fp &b) {
-    Fp d;
-    d.l[0] = sub_cc(a.l[0], b.l[0]);
-#pragma unroll
-    for (int i = 1; i < 12; i++) d.l[i] = subc_cc(a.l[i], b.l[i]);
-    uint32_t mask = subc(0, 0);
     Fp r;
-    r.l[0] = add_cc(d.l[0], ZKP_P[0] & mask);
 #pragma unroll
-    for (int i = 1; i < 11; i++) r.l[i] = addc_cc(d.l[i], ZKP_P[i] & mask);
-    r.l[11] = addc(d.l[11], ZKP_P[11] & mask);
+    for (int i = 0; i < ZKP_NL; i++) r.l[i] = a.l[i] - b.l[i];
+    ZKP_SETB(r, a.lb + b.lb, a.tb + b.tb, a.vb + b.vb);
     return r;
 }
-// a - b + p, for a in [0,2p), b in [0,p]: result in (0, 3p) -- no conditional; feeds a multiplier
-ZKP_HD Fp fp_sub_nr(const Fp &a, const Fp &b) {
-    Fp t;
-    t.l[0] = add_cc(a.l[0], ZKP_P[0]);
-#pragma unroll
-    for (int i = 1; i < 11; i++) t.l[i] = addc_cc(a.l[i], ZKP_P[i]);
-    t.l[11] = addc(a.l[11], ZKP_P[11]);
-    Fp r;
-    r.l[0] = sub_cc(t.l[0], b.l[0]);
-#pragma unroll
-    for (int i = 1; i < 11; i++) r.l[i] = subc_cc(t.l[i], b.l[i]);
-    r.l[11] = subc(t.l[11], b.l[11]);
-    return r;
-}
-// -a mod p  -- src/fp.rs:381-405 (zero stays zero)
+// -a                                         -- src/fp.rs:381-405
 ZKP_HD Fp fp_neg(const Fp &a) {
-    uint32_t nz = 0;
-#pragma unroll
-    for (int i = 0; i < 12; i++) nz |= a.l[i];
-    uint32_t mask = nz ? 0xffffffffu : 0u;
     Fp r;
-    r.l[0] = sub_cc(ZKP_P[0] & mask, a.l[0]);
 #pragma unroll
-    for (int i = 1; i < 11; i++) r.l[i] = subc_cc(ZKP_P[i] & mask, a.l[i]);
-    r.l[11] = subc(ZKP_P[11] & mask, a.l[11]);
+    for (int i = 0; i < ZKP_NL; i++) r.l[i] = -a.l[i];
+    ZKP_SETB(r, a.lb, a.tb, a.vb);
     return r;
 }
 ZKP_HD Fp fp_dbl(const Fp &a) { return fp_add(a, a); }
 
-// ------------------------------------------------------------------ Montgomery product
-//
-// Returns a*b/R mod p as a value in [0, 2p) whenever a*b < p*R; `a` (the operand multiplied
-// through every row) must be < 6p, `b` may be any 384-bit value.  See the file header for the
-// even/odd accumulator layout.
-
-// x[j..j+1] += k[j]*m for j = 0,2,..,10 (one carry chain, 6 wide MACs); leaves carry-out in CF
-template <int OFF>
-ZKP_HD void chain_mad(uint32_t *x, const uint32_t *k, uint32_t m) {
-    x[0] = mad_lo_cc(k[OFF], m, x[0]);
-    x[1] = madc_hi_cc(k[OFF], m, x[1]);
-#pragma unroll
-    for (int j = 2; j < 12; j += 2) {
-        x[j] = madc_lo_cc(k[j + OFF], m, x[j]);
-        x[j + 1] = madc_hi_cc(k[j + OFF], m, x[j + 1]);
-    }
-}
-// y >>= 64 bits; y[j..j+1] += a[j+1]*m for j = 0,2,..,10, consuming the incoming carry
-ZKP_HD void chain_mad_rshift(uint32_t *y, const uint32_t *a, uint32_t m) {
-#pragma unroll
-    for (int j = 0; j < 10; j += 2) {
-        y[j] = madc_lo_cc(a[j + 1], m, y[j + 2]);
-        y[j + 1] = madc_hi_cc(a[j + 1], m, y[j + 3]);
-    }
-    y[10] = madc_lo_cc(a[11], m, 0);
-    y[11] = madc_hi(a[11], m, 0);
-}
-// reduction half of a row: m = x0 * n0'; y += p_odd*m; x += p_even*m; carry of x into y[11]
-ZKP_HD void row_reduce(uint32_t *x, uint32_t *y) {
-    uint32_t m = x[0] * ZKP_N0INV;
-    chain_mad<1>(y, ZKP_P, m);
-    chain_mad<0>(x, ZKP_P, m);
-    y[11] = addc(y[11], 0);
-}
-// one full CIOS row (not the first): x = array in the even role, y = array in the odd role
-ZKP_HD void row_mul(uint32_t *x, uint32_t *y, const uint32_t *a, uint32_t bi) {
-    x[0] = add_cc(x[0], y[1]);
-    chain_mad_rshift(y, a, bi);
-    chain_mad<0>(x, a, bi);
-    y[11] = addc(y[11], 0);
-    row_reduce(x, y);
-}
-
-ZKP_HD Fp mont_mul_raw(const Fp &a, const Fp &b) {
-    uint32_t ev[12], od[12];
-    // row 0: disjoint 64-bit products, no carries
-#pragma unroll
-    for (int j = 0; j < 12; j += 2) {
-        uint64_t e = (uint64_t)a.l[j] * b.l[0];
-        uint64_t o = (uint64_t)a.l[j + 1] * b.l[0];
-        ev[j] = (uint32_t)e;
-        ev[j + 1] = (uint32_t)(e >> 32);
-        od[j] = (uint32_t)o;
-        od[j + 1] = (uint32_t)(o >> 32);
-    }
-    row_reduce(ev, od);
-#pragma unroll
-    for (int i = 1; i < 12; i += 2) {
-        row_mul(od, ev, a.l, b.l[i]);
-        if (i + 1 < 12) row_mul(ev, od, a.l, b.l[i + 1]);
-    }
-    // after row 11 the even role is `od` (od[0] == 0): T = ev + (od >> 32)
+// Weak normalization: one parallel carry round.  l[0..12] end in [-16, 2^28 + 16]; value unchanged.
+ZKP_HD Fp fp_wnorm(const Fp &a) {
     Fp r;
-    r.l[0] = add_cc(ev[0], od[1]);
+    r.l[0] = a.l[0] & ZKP_M28;
 #pragma unroll
-    for (int k = 1; k < 11; k++) r.l[k] = addc_cc(ev[k], od[k + 1]);
-    r.l[11] = addc(ev[11], 0);
+    for (int i = 1; i < ZKP_NL - 1; i++) r.l[i] = (a.l[i] & ZKP_M28) + (a.l[i - 1] >> 28);
+    r.l[ZKP_NL - 1] = a.l[ZKP_NL - 1] + (a.l[ZKP_NL - 2] >> 28);
+    ZKP_SETB(r, 268435456.0 + a.lb / 268435456.0 + 1.0, a.tb + a.lb / 268435456.0 + 1.0, a.vb);
+    return r;
+}
+// Full normalization: serial carry propagation.  l[0..12] end in [0, 2^28); l[13] takes the rest.
+ZKP_HD Fp fp_norm(const Fp &a) {
+    Fp r;
+    int32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < ZKP_NL - 1; i++) {
+        int32_t t = a.l[i] + c;
+        r.l[i] = t & ZKP_M28;
+        c = t >> 28;
+    }
+    r.l[ZKP_NL - 1] = a.l[ZKP_NL - 1] + c;
+    ZKP_SETB(r, 268435455.0, a.tb + a.lb / 268435456.0 + 1.0, a.vb);
     return r;
 }
 
-// Montgomery product, fully reduced to [0,p).  Inputs: a < 6p, a*b < p*R.
-// Value-equivalent (after conversion) to src/fp.rs:413-434.
-ZKP_HD Fp fp_mul(const Fp &a, const Fp &b) { return fp_reduce_once(mont_mul_raw(a, b)); }
-ZKP_HD Fp fp_sqr(const Fp &a) { return fp_mul(a, a); }   // src/fp.rs:452-455
-
-// canonical [0,p) limbs -> Montgomery form, and back
-ZKP_HD Fp fp_to_mont(const Fp &a) {
-    Fp r2;
+// Value reduction for the rare data paths that carry a value through additions only (the z terms
+// of the cyclotomic squaring): subtracts q*p with q = round(v/p) estimated from the top limb, so the
+// result lies in (-0.51p, 0.51p).  Any limb bound below 2^31 and |v| < 1000p are accepted: the
+// multiply-subtract runs in 64 bits (14 IMAD.WIDE) and one carry round brings the limbs back to
+// [-1026, 2^28 + 1026].
+#define ZKP_VREDUCE_K 10322781ll   /* round(2^404 / p) = 2^40 / (p / 2^364) */
+ZKP_HD Fp fp_vreduce(const Fp &a) {
+#ifdef ZKP_TRACK_BOUNDS
+    if (a.vb > 1000.0) zkp_bound_fail("fp_vreduce input value bound", a.vb);
+#endif
+    // the top limb only sees v / 2^364 after the lower limbs' carries are folded in
+    int32_t top = a.l[ZKP_NL - 1] + (a.l[ZKP_NL - 2] >> 28);
+    int32_t q = (int32_t)(((int64_t)top * ZKP_VREDUCE_K + (1ll << 39)) >> 40);
+    Fp r;
+    int64_t x = (int64_t)a.l[0] - (int64_t)q * ZKP_P[0];
+    r.l[0] = (int32_t)((uint32_t)x & ZKP_M28);
 #pragma unroll
-    for (int i = 0; i < 12; i++) r2.l[i] = ZKP_R2[i];
-    return fp_mul(a, r2);
+    for (int i = 1; i < ZKP_NL - 1; i++) {
+        int32_t c = (int32_t)(x >> 28);
+        x = (int64_t)a.l[i] - (int64_t)q * ZKP_P[i];
+        r.l[i] = (int32_t)((uint32_t)x & ZKP_M28) + c;
+    }
+    r.l[ZKP_NL - 1] = a.l[ZKP_NL - 1] - q * ZKP_P[ZKP_NL - 1] + (int32_t)(x >> 28);
+    ZKP_SETB(r, 268435456.0 + 1026.0, 0.51 * ZKP_TOP_PER_P + 1030.0, 0.52);
+    return r;
 }
-ZKP_HD Fp fp_from_mont(const Fp &a) {
+
+// ------------------------------------------------------------------ Montgomery product
+//
+// a*b/2^392 mod p as a normalized value in (ab/R, ab/R + p).  Separated operand scanning over 27
+// 64-bit column accumulators: 196 IMAD.WIDE for a*b, then per reduction step one IMAD (m) and 14
+// IMAD.WIDE.U32 (m*p); no carries anywhere, the columns are resolved by two shifts each.
+ZKP_HD Fp mont_mul(const Fp &a, const Fp &b) {
+#ifdef ZKP_TRACK_BOUNDS
+    {
+        double A = a.lb > a.tb ? a.lb : a.tb, B = b.lb > b.tb ? b.lb : b.tb;
+        double col = 14.0 * A * B + 14.0 * 72057594037927936.0 + 1099511627776.0;
+        if (col > g_max_col) g_max_col = col;
+        if (col >= 9.2e18) zkp_bound_fail("column accumulator reaches 2^63 in mont_mul", col);
+        if (a.vb * b.vb / ZKP_R_OVER_P + 1.0 > 2000.0) zkp_bound_fail("product value bound", a.vb * b.vb);
+    }
+#endif
+    int64_t col[2 * ZKP_NL - 1];
+#pragma unroll
+    for (int j = 0; j < ZKP_NL; j++) col[j] = (int64_t)a.l[0] * (int64_t)b.l[j];
+#pragma unroll
+    for (int i = 1; i < ZKP_NL; i++) {
+#pragma unroll
+        for (int j = 0; j < ZKP_NL - 1; j++) col[i + j] += (int64_t)a.l[i] * (int64_t)b.l[j];
+        col[i + ZKP_NL - 1] = (int64_t)a.l[i] * (int64_t)b.l[ZKP_NL - 1];
+    }
+    int64_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < ZKP_NL; k++) {
+        int64_t t = col[k] + carry;
+        uint32_t m = ((uint32_t)t * ZKP_N0INV) & ZKP_M28;
+        t += (int64_t)((uint64_t)m * (uint32_t)ZKP_P[0]);
+        carry = t >> 28;   // exact: the low 28 bits of t are zero now
+#pragma unroll
+        for (int j = 1; j < ZKP_NL; j++) col[k + j] += (int64_t)((uint64_t)m * (uint32_t)ZKP_P[j]);
+    }
+    Fp r;
+#pragma unroll
+    for (int k = ZKP_NL; k < 2 * ZKP_NL - 1; k++) {
+        int64_t t = col[k] + carry;
+        r.l[k - ZKP_NL] = (int32_t)((uint32_t)t & ZKP_M28);
+        carry = t >> 28;
+    }
+    r.l[ZKP_NL - 1] = (int32_t)carry;
+#ifdef ZKP_TRACK_BOUNDS
+    {
+        double vb = a.vb * b.vb / ZKP_R_OVER_P + 1.0;
+        ZKP_SETB(r, 268435455.0, vb * ZKP_TOP_PER_P + 2.0, vb);
+    }
+#endif
+    return r;
+}
+// Value-equivalent (after conversion) to src/fp.rs:413-434 / :452-455.
+ZKP_HD Fp fp_mul(const Fp &a, const Fp &b) { return mont_mul(a, b); }
+
+// ------------------------------------------------------------------ boundary conversions
+//
+// Canonical form = 12 saturated 32-bit words (= the six u64 limbs of src/fp.rs:24), value in [0,p).
+
+// true when w < p
+ZKP_HD bool words_lt_p(const uint32_t *w) {
+    int64_t borrow = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        int64_t d = (int64_t)w[i] - (int64_t)ZKP_P32[i] + borrow;
+        borrow = d >> 32;   // 0 or -1
+    }
+    return borrow != 0;
+}
+// canonical words -> Montgomery Fp; sets bad when w >= p (such inputs are rejected at the boundary
+// because the reference's neg is undefined there, src/fp.rs:383-405)
+ZKP_HD Fp fp_from_words(const uint32_t *w, bool &bad) {
+    bad = bad | !words_lt_p(w);
+    Fp a;
+#pragma unroll
+    for (int i = 0; i < ZKP_NL; i++) {
+        const int bit = 28 * i, idx = bit >> 5, sh = bit & 31;
+        uint32_t lo = w[idx] >> sh;
+        uint32_t hi = (sh > 4 && idx + 1 < 12) ? (w[idx + 1] << (32 - sh)) : 0u;
+        a.l[i] = (int32_t)((lo | hi) & ZKP_M28);
+    }
+    ZKP_SETB(a, 268435455.0, 16777216.0, 10.0);   // any 384-bit input (even a rejected one) stays in range
+    return mont_mul(a, fp_const(ZKP_R2));
+}
+// Montgomery Fp (any lazily reduced value the tracker allows) -> canonical words in [0,p)
+ZKP_HD void fp_to_words(uint32_t *w, const Fp &m) {
     Fp one = fp_zero();
     one.l[0] = 1;
-    return fp_mul(a, one);
+    ZKP_SETB(one, 1.0, 0.0, 1.0);
+    Fp t = mont_mul(m, one);                 // value in (-0.8p, 1.8p) for |m| < 2000p
+    t = fp_norm(fp_add(t, fp_const(ZKP_P))); // + p: strictly positive, fully normalized
+    uint64_t acc = 0;
+    int have = 0, wi = 0;
+    uint32_t v[13];
+#pragma unroll
+    for (int i = 0; i < ZKP_NL; i++) {
+        acc |= (uint64_t)(uint32_t)t.l[i] << have;
+        have += 28;
+        if (have >= 32) {
+            v[wi++] = (uint32_t)acc;
+            acc >>= 32;
+            have -= 32;
+        }
+    }
+    v[wi] = (uint32_t)acc;   // wi == 12 here; bits 384.. (zero: value < 3p < 2^384)
+    // value < 2.8p: two conditional subtractions of p
+#pragma unroll
+    for (int rep = 0; rep < 2; rep++) {
+        uint32_t d[12];
+        int64_t borrow = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            int64_t x = (int64_t)v[i] - (int64_t)ZKP_P32[i] + borrow;
+            d[i] = (uint32_t)x;
+            borrow = x >> 32;
+        }
+        bool ge = borrow == 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) v[i] = ge ? d[i] : v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) w[i] = v[i];
 }
-// true when the 12 limbs encode a value < p (boundary check; inputs >= p are rejected because the
-// reference's neg is undefined there, src/fp.rs:383-405)
-ZKP_HD bool fp_is_canonical(const Fp &a) {
-    Fp t;
-    return sub_limbs(t, a, ZKP_P) != 0;
+// Comparisons go through the canonical form (rare: flags and degenerate cases of the group law).
+ZKP_HD bool fp_is_zero(const Fp &a) {
+    uint32_t w[12];
+    fp_to_words(w, a);
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) t |= w[i];
+    return t == 0;
 }
 
 }  // namespace zkp

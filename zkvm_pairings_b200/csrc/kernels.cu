@@ -20,6 +20,7 @@
 
 #include "../../include/zkpair.h"
 #include "ops.cuh"
+#include "cios32_probe.cuh"
 
 #ifndef ZKP_TPB
 #define ZKP_TPB 128           // threads per block of the pairing kernels

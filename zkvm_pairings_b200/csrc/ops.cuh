@@ -35,27 +35,34 @@ ZKP_HOSTDEV void tower_op_shape(int op, int &na, int &nb, int &nr) {
 }
 
 // canonical u64 limbs -> Montgomery Fp.  Sets bad when the value is >= p.
-ZKP_HD Fp load_fp(const uint64_t *src, bool &bad) {
-    Fp a;
+ZKP_NOINLINE Fp load_fp(const uint64_t *src, bool &bad) {
+    uint32_t w[12];
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-        uint64_t w = src[i];
-        a.l[2 * i] = (uint32_t)w;
-        a.l[2 * i + 1] = (uint32_t)(w >> 32);
+        uint64_t x = src[i];
+        w[2 * i] = (uint32_t)x;
+        w[2 * i + 1] = (uint32_t)(x >> 32);
     }
-    bad = bad | !fp_is_canonical(a);
-    return fp_to_mont(a);
+    return fp_from_words(w, bad);
 }
-ZKP_HD void store_fp(uint64_t *dst, const Fp &m) {
-    Fp a = fp_from_mont(m);
+// Montgomery Fp -> canonical u64 limbs; returns the OR of all output words except the lowest and
+// writes the lowest to *low (so callers can test for 0 / 1 without another conversion)
+ZKP_NOINLINE uint32_t store_fp(uint64_t *dst, Fp m, uint32_t *low) {
+    uint32_t w[12];
+    fp_to_words(w, m);
+    uint32_t rest = 0;
 #pragma unroll
-    for (int i = 0; i < 6; i++) dst[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
+    for (int i = 0; i < 6; i++) dst[i] = (uint64_t)w[2 * i] | ((uint64_t)w[2 * i + 1] << 32);
+#pragma unroll
+    for (int i = 1; i < 12; i++) rest |= w[i];
+    if (low) *low = w[0];
+    return rest;
 }
 ZKP_HD void load_fps(Fp *dst, const uint64_t *src, int n, bool &bad) {
     for (int i = 0; i < n; i++) dst[i] = load_fp(src + 6 * i, bad);
 }
 ZKP_HD void store_fps(uint64_t *dst, const Fp *src, int n) {
-    for (int i = 0; i < n; i++) store_fp(dst + 6 * i, src[i]);
+    for (int i = 0; i < n; i++) store_fp(dst + 6 * i, src[i], nullptr);
 }
 
 // One element of a batched tower op.  a/b/out point at this element's limbs.  Returns a status
@@ -128,7 +135,19 @@ ZKP_HD void load_g2(G2A &q, const uint64_t *xy, bool &bad) {
     q.x.c0 = load_fp(xy, bad); q.x.c1 = load_fp(xy + 6, bad);
     q.y.c0 = load_fp(xy + 12, bad); q.y.c1 = load_fp(xy + 18, bad);
 }
-ZKP_HD void store_fp12(uint64_t *dst, const Fp12 &f) { store_fps(dst, &f.c0.c0.c0, 12); }
+// stores f and returns true when it equals Fp12::one() (canonical 1, 0, ..., 0)
+ZKP_HD bool store_fp12(uint64_t *dst, const Fp12 &f) {
+    const Fp *c = &f.c0.c0.c0;
+    uint32_t low = 0, rest = 0;
+    rest |= store_fp(dst, c[0], &low);
+    bool one = (low == 1u);
+    for (int i = 1; i < 12; i++) {
+        uint32_t l2 = 0;
+        rest |= store_fp(dst + 6 * i, c[i], &l2);
+        rest |= l2;
+    }
+    return one & (rest == 0);
+}
 ZKP_HD void load_fp12(Fp12 &f, const uint64_t *src, bool &bad) { load_fps(&f.c0.c0.c0, src, 12, bad); }
 
 // mode bits for pairing_one
@@ -158,8 +177,8 @@ ZKP_HD uint8_t pairing_one(int mode, const uint64_t *g1, const uint8_t *g1inf, c
         load_fp12(f, in12, bad);
     }
     if (mode & ZKP_DO_FINAL_EXP) final_exponentiation(f, f);
-    store_fp12(out, f);
-    if (is_one) *is_one = fp12_is_one(f) ? 1 : 0;
+    bool one = store_fp12(out, f);
+    if (is_one) *is_one = one ? 1 : 0;
     return bad ? 1 : 0;
 }
 
@@ -173,23 +192,18 @@ ZKP_HD uint64_t splitmix64_at(uint64_t seed, uint64_t idx) {
 
 // [k]G for the G1 / G2 generators, k = 64-bit scalar (synthetic input generation, untimed)
 ZKP_HD void gen_g1_one(uint64_t k, uint64_t *xy, uint8_t *inf) {
-    Fp gx, gy, ax, ay;
-#pragma unroll
-    for (int i = 0; i < 12; i++) { gx.l[i] = ZKP_G1_GEN[i]; gy.l[i] = ZKP_G1_GEN[12 + i]; }
+    Fp gx = fp_const(ZKP_G1_GEN), gy = fp_const(ZKP_G1_GEN + ZKP_NL), ax, ay;
     *inf = scalar_mul_affine<OpsFp>(ax, ay, gx, gy, &k, 64) ? 1 : 0;
-    store_fp(xy, ax);
-    store_fp(xy + 6, ay);
+    store_fp(xy, ax, nullptr);
+    store_fp(xy + 6, ay, nullptr);
 }
 ZKP_HD void gen_g2_one(uint64_t k, uint64_t *xy, uint8_t *inf) {
     Fp2 gx, gy, ax, ay;
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-        gx.c0.l[i] = ZKP_G2_GEN[i]; gx.c1.l[i] = ZKP_G2_GEN[12 + i];
-        gy.c0.l[i] = ZKP_G2_GEN[24 + i]; gy.c1.l[i] = ZKP_G2_GEN[36 + i];
-    }
+    gx.c0 = fp_const(ZKP_G2_GEN); gx.c1 = fp_const(ZKP_G2_GEN + ZKP_NL);
+    gy.c0 = fp_const(ZKP_G2_GEN + 2 * ZKP_NL); gy.c1 = fp_const(ZKP_G2_GEN + 3 * ZKP_NL);
     *inf = scalar_mul_affine<OpsFp2>(ax, ay, gx, gy, &k, 64) ? 1 : 0;
-    store_fp(xy, ax.c0); store_fp(xy + 6, ax.c1);
-    store_fp(xy + 12, ay.c0); store_fp(xy + 18, ay.c1);
+    store_fp(xy, ax.c0, nullptr); store_fp(xy + 6, ax.c1, nullptr);
+    store_fp(xy + 12, ay.c0, nullptr); store_fp(xy + 18, ay.c1, nullptr);
 }
 
 }  // namespace zkp

@@ -6,11 +6,18 @@
 // Fp6 mul = 6 Fp2 mul, Fp12 mul = 3 Fp6 mul) instead of the reference's schoolbook Fp2
 // (src/fp2.rs:192-209) and 36-mul interleaved Fp6 (src/fp6.rs:188-267).
 //
-// Code-size / register strategy: the 300-MAC Montgomery product is ONE out-of-line function
-// (fmul) whose operands and result travel in registers (24 in, 12 out -- verified in SASS: no
-// stack traffic), so its ~5 KB body stays hot in the instruction cache and every call site is
-// ~40 instructions.  Fp/Fp2 additions are inlined; Fp6-level and larger operations are
-// out-of-line and exchange operands through thread-local memory (L1-resident).
+// Code-size / register strategy: the 420-IMAD Montgomery product is ONE out-of-line function
+// (fmul) whose operands and result travel in registers (28 in, 14 out -- verified in SASS: no
+// stack traffic), so its body stays hot in the instruction cache and every call site is a few
+// dozen instructions.  Fp/Fp2 additions are inlined (14 carry-free adds per Fp); Fp6-level and
+// larger operations are out-of-line and exchange operands through thread-local memory.
+//
+// Lazy reduction: additions never reduce; products come back normalized.  Every Fp2
+// product/square weakly normalizes its outputs (fp_wnorm, one parallel carry round) so limb
+// magnitudes stay far below 2^31, and every Fp6-level function value-reduces its outputs
+// (fp_vreduce, |v| < 0.52p) so the value bounds cannot compound through chains of products.  The
+// bound tracker of the CPU dev simulation (ZKP_TRACK_BOUNDS) proves the worst case over the whole
+// pairing: the bounds depend on the formula DAG only, never on the data.
 #pragma once
 #include "fp.cuh"
 
@@ -26,8 +33,9 @@ ZKP_NOINLINE Fp fp_inv(Fp a) {
     Fp res = a;   // bit 380 of p-2 is set
     for (int i = 379; i >= 0; i--) {
         res = fsqr(res);
-        uint32_t w = ZKP_P[i >> 5] - ((i >> 5) == 0 ? 2u : 0u);   // limbs of p-2 (no borrow: p0 = ...aaab)
-        if ((w >> (i & 31)) & 1) res = fmul(res, a);
+        int limb = i / 28;
+        uint32_t w = (uint32_t)ZKP_P[limb] - (limb == 0 ? 2u : 0u);   // limbs of p-2 (no borrow: p0 = ...aaab)
+        if ((w >> (i - 28 * limb)) & 1) res = fmul(res, a);
     }
     return res;
 }
@@ -40,7 +48,8 @@ struct Fp2 {
 ZKP_HD Fp2 fp2_zero() { Fp2 r; r.c0 = fp_zero(); r.c1 = fp_zero(); return r; }
 ZKP_HD Fp2 fp2_one() { Fp2 r; r.c0 = fp_one(); r.c1 = fp_zero(); return r; }
 ZKP_HD bool fp2_is_zero(const Fp2 &a) { return fp_is_zero(a.c0) & fp_is_zero(a.c1); }
-ZKP_HD bool fp2_eq(const Fp2 &a, const Fp2 &b) { return fp_eq(a.c0, b.c0) & fp_eq(a.c1, b.c1); }
+ZKP_HD Fp2 fp2_vreduce(const Fp2 &a) { Fp2 r; r.c0 = fp_vreduce(a.c0); r.c1 = fp_vreduce(a.c1); return r; }
+ZKP_HD Fp2 fp2_wnorm(const Fp2 &a) { Fp2 r; r.c0 = fp_wnorm(a.c0); r.c1 = fp_wnorm(a.c1); return r; }
 ZKP_HD Fp2 fp2_add(const Fp2 &a, const Fp2 &b) { Fp2 r; r.c0 = fp_add(a.c0, b.c0); r.c1 = fp_add(a.c1, b.c1); return r; }   // src/fp2.rs:216-218
 ZKP_HD Fp2 fp2_sub(const Fp2 &a, const Fp2 &b) { Fp2 r; r.c0 = fp_sub(a.c0, b.c0); r.c1 = fp_sub(a.c1, b.c1); return r; }   // src/fp2.rs:221-223
 ZKP_HD Fp2 fp2_neg(const Fp2 &a) { Fp2 r; r.c0 = fp_neg(a.c0); r.c1 = fp_neg(a.c1); return r; }                            // src/fp2.rs:226-228
@@ -48,22 +57,23 @@ ZKP_HD Fp2 fp2_dbl(const Fp2 &a) { return fp2_add(a, a); }
 ZKP_HD Fp2 fp2_conj(const Fp2 &a) { Fp2 r; r.c0 = a.c0; r.c1 = fp_neg(a.c1); return r; }                                  // src/fp2.rs:155-157
 // (a + bu)(1 + u) = (a - b) + (a + b)u   -- src/fp2.rs:161-168
 ZKP_HD Fp2 fp2_mul_nr(const Fp2 &a) { Fp2 r; r.c0 = fp_sub(a.c0, a.c1); r.c1 = fp_add(a.c0, a.c1); return r; }
-// Karatsuba, 3 Fp mul (value-equal to the schoolbook src/fp2.rs:192-209)
+// Karatsuba, 3 Fp mul (value-equal to the schoolbook src/fp2.rs:192-209).  Both operands must be
+// (weakly) normalized: the middle product multiplies two sums of two limbs, 14*(2N)*(2N) < 2^63.
+// Output weakly normalized.
 ZKP_HD Fp2 fp2_mul(const Fp2 &a, const Fp2 &b) {
     Fp t0 = fmul(a.c0, b.c0);
     Fp t1 = fmul(a.c1, b.c1);
-    Fp s = fmul(fp_add_nr(a.c0, a.c1), fp_add_nr(b.c0, b.c1));   // operands < 2p: product < p*R
+    Fp s = fmul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
     Fp2 r;
-    r.c0 = fp_sub(t0, t1);
-    r.c1 = fp_sub(fp_sub(s, t0), t1);
+    r.c0 = fp_wnorm(fp_sub(t0, t1));
+    r.c1 = fp_wnorm(fp_sub(fp_sub(s, t0), t1));
     return r;
 }
-// complex squaring, 2 Fp mul  -- src/fp2.rs:171-189
+// complex squaring, 2 Fp mul  -- src/fp2.rs:171-189 ; products come back normalized
 ZKP_HD Fp2 fp2_sqr(const Fp2 &a) {
     Fp2 r;
-    Fp d = fp_sub(a.c0, a.c1);
-    r.c0 = fmul(fp_add_nr(a.c0, a.c1), d);
-    r.c1 = fmul(fp_add_nr(a.c0, a.c0), a.c1);
+    r.c0 = fmul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1));
+    r.c1 = fmul(fp_dbl(a.c0), a.c1);
     return r;
 }
 ZKP_HD Fp2 fp2_mul_fp(const Fp2 &a, const Fp &k) { Fp2 r; r.c0 = fmul(a.c0, k); r.c1 = fmul(a.c1, k); return r; }   // src/fp2.rs:95-102
@@ -81,6 +91,8 @@ struct Fp6 {
     Fp2 c0, c1, c2;
 };
 
+ZKP_HD void fp6_vreduce(Fp6 &r, const Fp6 &a) { r.c0 = fp2_vreduce(a.c0); r.c1 = fp2_vreduce(a.c1); r.c2 = fp2_vreduce(a.c2); }
+ZKP_HD void fp6_wnorm(Fp6 &r, const Fp6 &a) { r.c0 = fp2_wnorm(a.c0); r.c1 = fp2_wnorm(a.c1); r.c2 = fp2_wnorm(a.c2); }
 ZKP_HD void fp6_set_zero(Fp6 &r) { r.c0 = fp2_zero(); r.c1 = fp2_zero(); r.c2 = fp2_zero(); }
 ZKP_HD void fp6_add(Fp6 &r, const Fp6 &a, const Fp6 &b) { r.c0 = fp2_add(a.c0, b.c0); r.c1 = fp2_add(a.c1, b.c1); r.c2 = fp2_add(a.c2, b.c2); }   // src/fp6.rs:322-333
 ZKP_HD void fp6_sub(Fp6 &r, const Fp6 &a, const Fp6 &b) { r.c0 = fp2_sub(a.c0, b.c0); r.c1 = fp2_sub(a.c1, b.c1); r.c2 = fp2_sub(a.c2, b.c2); }   // src/fp6.rs:358-367
@@ -97,31 +109,31 @@ ZKP_NOINLINE void fp6_mul(Fp6 &r, const Fp6 &a, const Fp6 &b) {
     Fp2 v0 = fp2_mul(a.c0, b.c0);
     Fp2 v1 = fp2_mul(a.c1, b.c1);
     Fp2 v2 = fp2_mul(a.c2, b.c2);
-    Fp2 t0 = fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c1, a.c2), fp2_add(b.c1, b.c2)), v1), v2);
-    Fp2 t1 = fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c0, a.c1), fp2_add(b.c0, b.c1)), v0), v1);
-    Fp2 t2 = fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c0, a.c2), fp2_add(b.c0, b.c2)), v0), v2);
-    r.c0 = fp2_add(v0, fp2_mul_nr(t0));
-    r.c1 = fp2_add(t1, fp2_mul_nr(v2));
-    r.c2 = fp2_add(t2, v1);
+    Fp2 t0 = fp2_sub(fp2_sub(fp2_mul(fp2_wnorm(fp2_add(a.c1, a.c2)), fp2_wnorm(fp2_add(b.c1, b.c2))), v1), v2);
+    Fp2 t1 = fp2_sub(fp2_sub(fp2_mul(fp2_wnorm(fp2_add(a.c0, a.c1)), fp2_wnorm(fp2_add(b.c0, b.c1))), v0), v1);
+    Fp2 t2 = fp2_sub(fp2_sub(fp2_mul(fp2_wnorm(fp2_add(a.c0, a.c2)), fp2_wnorm(fp2_add(b.c0, b.c2))), v0), v2);
+    r.c0 = fp2_vreduce(fp2_add(v0, fp2_mul_nr(t0)));
+    r.c1 = fp2_vreduce(fp2_add(t1, fp2_mul_nr(v2)));
+    r.c2 = fp2_vreduce(fp2_add(t2, v1));
 }
 // src/fp6.rs:274-288 ; r may alias a
 ZKP_NOINLINE void fp6_sqr(Fp6 &r, const Fp6 &a) {
     Fp2 s0 = fp2_sqr(a.c0);
     Fp2 ab = fp2_mul(a.c0, a.c1);
     Fp2 s1 = fp2_dbl(ab);
-    Fp2 s2 = fp2_sqr(fp2_add(fp2_sub(a.c0, a.c1), a.c2));
+    Fp2 s2 = fp2_sqr(fp2_wnorm(fp2_add(fp2_sub(a.c0, a.c1), a.c2)));
     Fp2 bc = fp2_mul(a.c1, a.c2);
     Fp2 s3 = fp2_dbl(bc);
     Fp2 s4 = fp2_sqr(a.c2);
-    r.c0 = fp2_add(fp2_mul_nr(s3), s0);
-    r.c1 = fp2_add(fp2_mul_nr(s4), s1);
-    r.c2 = fp2_sub(fp2_sub(fp2_add(fp2_add(s1, s2), s3), s0), s4);
+    r.c0 = fp2_vreduce(fp2_add(fp2_mul_nr(s3), s0));
+    r.c1 = fp2_vreduce(fp2_add(fp2_mul_nr(s4), s1));
+    r.c2 = fp2_vreduce(fp2_sub(fp2_sub(fp2_add(fp2_add(s1, s2), s3), s0), s4));
 }
 // a * (0, c1, 0)  -- src/fp6.rs:102-108 ; r may alias a
 ZKP_NOINLINE void fp6_mul_by_1(Fp6 &r, const Fp6 &a, const Fp2 &c1) {
-    Fp2 t0 = fp2_mul_nr(fp2_mul(a.c2, c1));
-    Fp2 t1 = fp2_mul(a.c0, c1);
-    Fp2 t2 = fp2_mul(a.c1, c1);
+    Fp2 t0 = fp2_vreduce(fp2_mul_nr(fp2_mul(a.c2, c1)));
+    Fp2 t1 = fp2_vreduce(fp2_mul(a.c0, c1));
+    Fp2 t2 = fp2_vreduce(fp2_mul(a.c1, c1));
     r.c0 = t0; r.c1 = t1; r.c2 = t2;
 }
 // a * (c0, c1, 0)  -- src/fp6.rs:110-125 ; r may alias a
@@ -129,20 +141,20 @@ ZKP_NOINLINE void fp6_mul_by_01(Fp6 &r, const Fp6 &a, const Fp2 &c0, const Fp2 &
     Fp2 a_a = fp2_mul(a.c0, c0);
     Fp2 b_b = fp2_mul(a.c1, c1);
     Fp2 t1 = fp2_add(fp2_mul_nr(fp2_mul(a.c2, c1)), a_a);
-    Fp2 t2 = fp2_sub(fp2_sub(fp2_mul(fp2_add(c0, c1), fp2_add(a.c0, a.c1)), a_a), b_b);
+    Fp2 t2 = fp2_sub(fp2_sub(fp2_mul(fp2_wnorm(fp2_add(c0, c1)), fp2_wnorm(fp2_add(a.c0, a.c1))), a_a), b_b);
     Fp2 t3 = fp2_add(fp2_mul(a.c2, c0), b_b);
-    r.c0 = t1; r.c1 = t2; r.c2 = t3;
+    r.c0 = fp2_vreduce(t1); r.c1 = fp2_vreduce(t2); r.c2 = fp2_vreduce(t3);
 }
 // src/fp6.rs:291-309 ; zero maps to zero ; r may alias a
 ZKP_NOINLINE void fp6_inv(Fp6 &r, const Fp6 &a) {
-    Fp2 c0 = fp2_sub(fp2_sqr(a.c0), fp2_mul_nr(fp2_mul(a.c1, a.c2)));
-    Fp2 c1 = fp2_sub(fp2_mul_nr(fp2_sqr(a.c2)), fp2_mul(a.c0, a.c1));
-    Fp2 c2 = fp2_sub(fp2_sqr(a.c1), fp2_mul(a.c0, a.c2));
+    Fp2 c0 = fp2_wnorm(fp2_sub(fp2_sqr(a.c0), fp2_mul_nr(fp2_mul(a.c1, a.c2))));
+    Fp2 c1 = fp2_wnorm(fp2_sub(fp2_mul_nr(fp2_sqr(a.c2)), fp2_mul(a.c0, a.c1)));
+    Fp2 c2 = fp2_wnorm(fp2_sub(fp2_sqr(a.c1), fp2_mul(a.c0, a.c2)));
     Fp2 t = fp2_mul_nr(fp2_add(fp2_mul(a.c1, c2), fp2_mul(a.c2, c1)));
-    t = fp2_inv(fp2_add(t, fp2_mul(a.c0, c0)));
-    r.c0 = fp2_mul(t, c0);
-    r.c1 = fp2_mul(t, c1);
-    r.c2 = fp2_mul(t, c2);
+    t = fp2_inv(fp2_wnorm(fp2_add(t, fp2_mul(a.c0, c0))));
+    r.c0 = fp2_vreduce(fp2_mul(t, c0));
+    r.c1 = fp2_vreduce(fp2_mul(t, c1));
+    r.c2 = fp2_vreduce(fp2_mul(t, c2));
 }
 
 // ------------------------------------------------------------------ Fp12
@@ -152,53 +164,55 @@ struct Fp12 {
 
 ZKP_HD void fp12_set_one(Fp12 &r) { fp6_set_zero(r.c0); fp6_set_zero(r.c1); r.c0.c0.c0 = fp_one(); }
 ZKP_HD void fp12_conj(Fp12 &r, const Fp12 &a) { r.c0 = a.c0; fp6_neg(r.c1, a.c1); }   // src/fp12.rs:123-125
-ZKP_HD bool fp12_is_one(const Fp12 &a) {
-    Fp12 o;
-    fp12_set_one(o);
-    const Fp *x = &a.c0.c0.c0, *y = &o.c0.c0.c0;
-    bool e = true;
-#pragma unroll
-    for (int i = 0; i < 12; i++) e = e & fp_eq(x[i], y[i]);
-    return e;
-}
 // Karatsuba over Fp6, 3 Fp6 mul  -- src/fp12.rs:193-210 ; r may alias a or b
 ZKP_NOINLINE void fp12_mul(Fp12 &r, const Fp12 &a, const Fp12 &b) {
     Fp6 aa, bb, sa, sb;
     fp6_mul(aa, a.c0, b.c0);
     fp6_mul(bb, a.c1, b.c1);
     fp6_add(sa, a.c1, a.c0);
+    fp6_wnorm(sa, sa);
     fp6_add(sb, b.c0, b.c1);
+    fp6_wnorm(sb, sb);
     fp6_mul(sa, sa, sb);
     fp6_sub(sa, sa, aa);
-    fp6_sub(r.c1, sa, bb);
+    fp6_sub(sa, sa, bb);
+    fp6_wnorm(r.c1, sa);
     fp6_mul_nr(bb, bb);
-    fp6_add(r.c0, bb, aa);
+    fp6_add(bb, bb, aa);
+    fp6_wnorm(r.c0, bb);
 }
 // complex squaring, 2 Fp6 mul  -- src/fp12.rs:173-184 ; r may alias a
 ZKP_NOINLINE void fp12_sqr(Fp12 &r, const Fp12 &a) {
     Fp6 ab, s, t;
     fp6_mul(ab, a.c0, a.c1);
     fp6_add(s, a.c0, a.c1);
+    fp6_wnorm(s, s);
     fp6_mul_nr(t, a.c1);
     fp6_add(t, t, a.c0);
+    fp6_wnorm(t, t);
     fp6_mul(t, t, s);
     fp6_sub(t, t, ab);
-    fp6_add(r.c1, ab, ab);
+    fp6_add(s, ab, ab);
+    fp6_wnorm(r.c1, s);
     fp6_mul_nr(ab, ab);
-    fp6_sub(r.c0, t, ab);
+    fp6_sub(t, t, ab);
+    fp6_wnorm(r.c0, t);
 }
 // f * (c0 + c1 v + c4 v w): sparse line multiplication  -- src/fp12.rs:99-111 ; in place
 ZKP_NOINLINE void fp12_mul_by_014(Fp12 &f, const Fp2 &c0, const Fp2 &c1, const Fp2 &c4) {
     Fp6 aa, bb, t;
     fp6_mul_by_01(aa, f.c0, c0, c1);
     fp6_mul_by_1(bb, f.c1, c4);
-    Fp2 o = fp2_add(c1, c4);
+    Fp2 o = fp2_wnorm(fp2_add(c1, c4));
     fp6_add(t, f.c1, f.c0);
+    fp6_wnorm(t, t);
     fp6_mul_by_01(t, t, c0, o);
     fp6_sub(t, t, aa);
-    fp6_sub(f.c1, t, bb);
+    fp6_sub(t, t, bb);
+    fp6_wnorm(f.c1, t);
     fp6_mul_nr(bb, bb);
-    fp6_add(f.c0, bb, aa);
+    fp6_add(bb, bb, aa);
+    fp6_wnorm(f.c0, bb);
 }
 // src/fp12.rs:186-190 ; zero maps to zero ; r may alias a
 ZKP_NOINLINE void fp12_inv(Fp12 &r, const Fp12 &a) {
@@ -207,6 +221,7 @@ ZKP_NOINLINE void fp12_inv(Fp12 &r, const Fp12 &a) {
     fp6_sqr(t1, a.c1);
     fp6_mul_nr(t1, t1);
     fp6_sub(t0, t0, t1);
+    fp6_wnorm(t0, t0);
     fp6_inv(t0, t0);
     fp6_mul(r.c0, a.c0, t0);
     fp6_neg(t0, t0);
@@ -219,18 +234,15 @@ ZKP_NOINLINE void fp12_inv(Fp12 &r, const Fp12 &a) {
 ZKP_NOINLINE void fp12_frobenius(Fp12 &r, const Fp12 &a, int k) {
     const Fp2 *src[6] = {&a.c0.c0, &a.c1.c0, &a.c0.c1, &a.c1.c1, &a.c0.c2, &a.c1.c2};
     Fp2 *dst[6] = {&r.c0.c0, &r.c1.c0, &r.c0.c1, &r.c1.c1, &r.c0.c2, &r.c1.c2};
-    const uint32_t *tab = ZKP_FROB + (k - 1) * 120;
+    const int32_t *tab = ZKP_FROB + (k - 1) * (10 * ZKP_NL);
 #pragma unroll 1
     for (int i = 0; i < 6; i++) {
         Fp2 c = *src[i];
         if (k & 1) c = fp2_conj(c);
         if (i > 0) {
             Fp2 g;
-#pragma unroll
-            for (int j = 0; j < 12; j++) {
-                g.c0.l[j] = tab[(i - 1) * 24 + j];
-                g.c1.l[j] = tab[(i - 1) * 24 + 12 + j];
-            }
+            g.c0 = fp_const(tab + (i - 1) * 2 * ZKP_NL);
+            g.c1 = fp_const(tab + (i - 1) * 2 * ZKP_NL + ZKP_NL);
             c = fp2_mul(c, g);
         }
         *dst[i] = c;
@@ -238,38 +250,44 @@ ZKP_NOINLINE void fp12_frobenius(Fp12 &r, const Fp12 &a, int k) {
 }
 
 // Granger-Scott squaring in the cyclotomic subgroup: 9 Fp2 squarings.  r may alias f.
+// The inputs z enter the outputs linearly (z' = 3t -+ 2z), so unlike everywhere else the value is
+// not renewed by a product: fp2_vreduce re-centres the z-carrying term each time, so the value
+// bounds reach a fixed point (|z'| < 8p) across the 63-step chains of cyclotomic_exp.
 ZKP_HD void fp4_square(Fp2 &c0, Fp2 &c1, const Fp2 &a, const Fp2 &b) {
     Fp2 t0 = fp2_sqr(a);
     Fp2 t1 = fp2_sqr(b);
-    c0 = fp2_add(fp2_mul_nr(t1), t0);
-    c1 = fp2_sub(fp2_sub(fp2_sqr(fp2_add(a, b)), t0), t1);
+    c0 = fp2_wnorm(fp2_add(fp2_mul_nr(t1), t0));
+    c1 = fp2_wnorm(fp2_sub(fp2_sub(fp2_sqr(fp2_wnorm(fp2_add(a, b))), t0), t1));
+}
+// 3t - 2z = 2(t - z) + t  and  3t + 2z = 2(t + z) + t, with the z-carrying term value-reduced
+ZKP_HD Fp2 cyc_minus(const Fp2 &t, const Fp2 &z) {
+    Fp2 w = fp2_vreduce(fp2_sub(t, z));
+    return fp2_wnorm(fp2_add(fp2_dbl(w), t));
+}
+ZKP_HD Fp2 cyc_plus(const Fp2 &t, const Fp2 &z) {
+    Fp2 w = fp2_vreduce(fp2_add(t, z));
+    return fp2_wnorm(fp2_add(fp2_dbl(w), t));
 }
 ZKP_NOINLINE void fp12_cyclotomic_sqr(Fp12 &r, const Fp12 &f) {
-    Fp2 t0, t1, z;
+    Fp2 t0, t1;
     // (z0, z1) = (c0.c0, c1.c1)
     {
         Fp2 z0 = f.c0.c0, z1 = f.c1.c1;
         fp4_square(t0, t1, z0, z1);
-        z = fp2_sub(t0, z0);
-        r.c0.c0 = fp2_add(fp2_dbl(z), t0);
-        z = fp2_add(t1, z1);
-        r.c1.c1 = fp2_add(fp2_dbl(z), t1);
+        r.c0.c0 = cyc_minus(t0, z0);
+        r.c1.c1 = cyc_plus(t1, z1);
     }
-    // (z2, z3) = (c1.c0, c0.c2) feeds z4' , z5' ; (z4, z5) = (c0.c1, c1.c2) feeds z2', z3'
+    // (z2, z3) = (c1.c0, c0.c2) feeds z4', z5' ; (z4, z5) = (c0.c1, c1.c2) feeds z2', z3'
     {
         Fp2 z2 = f.c1.c0, z3 = f.c0.c2, z4 = f.c0.c1, z5 = f.c1.c2;
         Fp2 t2, t3;
         fp4_square(t0, t1, z2, z3);
         fp4_square(t2, t3, z4, z5);
-        z = fp2_sub(t0, z4);
-        r.c0.c1 = fp2_add(fp2_dbl(z), t0);
-        z = fp2_add(t1, z5);
-        r.c1.c2 = fp2_add(fp2_dbl(z), t1);
-        t0 = fp2_mul_nr(t3);
-        z = fp2_add(t0, z2);
-        r.c1.c0 = fp2_add(fp2_dbl(z), t0);
-        z = fp2_sub(t2, z3);
-        r.c0.c2 = fp2_add(fp2_dbl(z), t2);
+        r.c0.c1 = cyc_minus(t0, z4);
+        r.c1.c2 = cyc_plus(t1, z5);
+        t0 = fp2_wnorm(fp2_mul_nr(t3));
+        r.c1.c0 = cyc_plus(t0, z2);
+        r.c0.c2 = cyc_minus(t2, z3);
     }
 }
 
