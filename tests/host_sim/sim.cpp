@@ -1,49 +1,102 @@
 // DEV SIMULATION of the device code for the CPU ("not gpu") test-suite.
 //
 // Compiles the very same headers the CUDA kernels are built from (zkvm_pairings_b200/csrc/*.cuh)
-// as plain C++ with the PTX carry flag emulated (fp.cuh, ZKP_HOST_SIM), so the limb-level
-// Montgomery algorithm, the tower and the pairing control flow can be checked against the oracle
-// without a GPU.  TEST INFRASTRUCTURE ONLY: it is built into tests/host_sim/libzkpair_sim.so, is
-// never linked into or loaded by libzkpair.so / the zkvm_pairings_b200 package, and is not a CPU
-// fallback (the product path raises when the CUDA library or a GPU is missing).
+// as plain C++, so the limb-level Montgomery arithmetic, the lazy-reduction bounds
+// (-DZKP_TRACK_BOUNDS), the tower and the pairing control flow can be checked against the oracle
+// without a GPU.  The two lanes that share one pairing on the device are two host threads in
+// lock-step here; the shfl.xor exchange is a two-party rendezvous.  TEST INFRASTRUCTURE ONLY: built
+// into tests/host_sim/libzkpair_sim*.so, never linked into or loaded by libzkpair.so / the
+// zkvm_pairings_b200 package, and not a CPU fallback (the product path raises when the CUDA
+// library or a GPU is missing).
 #define ZKP_HOST_SIM 1
 #include <stddef.h>
+#include <string.h>
+
+#include <atomic>
+#include <thread>
+
 #include "../../zkvm_pairings_b200/csrc/ops.cuh"
 
+namespace zkp {
+thread_local int zkp_sim_par = 0;
+static std::atomic<int> g_arrived{0};
+static std::atomic<int> g_phase{0};
+static unsigned char g_slot[2][512];
+static void pair_barrier() {
+    int ph = g_phase.load(std::memory_order_acquire);
+    if (g_arrived.fetch_add(1, std::memory_order_acq_rel) == 1) {
+        g_arrived.store(0, std::memory_order_relaxed);
+        g_phase.store(ph + 1, std::memory_order_release);
+    } else {
+        int spins = 0;
+        while (g_phase.load(std::memory_order_acquire) == ph)
+            if (++spins > 2000) std::this_thread::yield();
+    }
+}
+void zkp_sim_xchg(void *buf, unsigned long bytes) {
+    memcpy(g_slot[zkp_sim_par], buf, bytes);
+    pair_barrier();
+    memcpy(buf, g_slot[zkp_sim_par ^ 1], bytes);
+    pair_barrier();
+}
+int32_t zkp_sim_word_xchg(int32_t v) {
+    zkp_sim_xchg(&v, sizeof v);
+    return v;
+}
+}  // namespace zkp
+
 using namespace zkp;
+
+// run f() on both lanes of a pair (this thread = even lane, a helper thread = odd lane)
+template <class F>
+static void run_pair(F f) {
+    std::thread odd([&]() {
+        zkp_sim_par = 1;
+        f();
+    });
+    zkp_sim_par = 0;
+    f();
+    odd.join();
+}
 
 extern "C" {
 int sim_tower_op(int op, const uint64_t *a, const uint64_t *b, uint64_t *out, uint8_t *status, size_t n) {
     int na, nb, nr;
     tower_op_shape(op, na, nb, nr);
-    for (size_t i = 0; i < n; i++) {
-        uint8_t s = tower_op_one(op, a + 6 * na * i, b ? b + 6 * nb * i : nullptr, out + 6 * nr * i);
-        if (status) status[i] = s;
-    }
+    run_pair([&]() {
+        for (size_t i = 0; i < n; i++) {
+            uint8_t s = tower_op_one(op, a + 6 * na * i, b ? b + 6 * nb * i : nullptr, out + 6 * nr * i);
+            if (status && lane_par() == 0) status[i] = s;
+        }
+    });
     return 0;
 }
 int sim_pairing(int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
                 size_t n, int k, const uint64_t *in12, uint64_t *out, uint8_t *is_one) {
-    int bad = 0;
-    for (size_t i = 0; i < n; i++) {
-        size_t e = i * (size_t)k;
-        bad |= pairing_one<8>(mode, g1 ? g1 + 12 * e : nullptr, g1inf ? g1inf + e : nullptr, g2 ? g2 + 24 * e : nullptr,
-                           g2inf ? g2inf + e : nullptr, k, in12 ? in12 + 72 * i : nullptr, out + 72 * i,
-                           is_one ? is_one + i : nullptr);
-    }
-    return bad ? -1 : 0;
+    std::atomic<int> bad{0};
+    run_pair([&]() {
+        for (size_t i = 0; i < n; i++) {
+            size_t e = i * (size_t)k;
+            if (pairing_one<8>(mode, g1 ? g1 + 12 * e : nullptr, g1inf ? g1inf + e : nullptr, g2 ? g2 + 24 * e : nullptr,
+                               g2inf ? g2inf + e : nullptr, k, in12 ? in12 + 72 * i : nullptr, out + 72 * i,
+                               is_one ? is_one + i : nullptr))
+                bad.store(1);
+        }
+    });
+    return bad.load() ? -1 : 0;
 }
 uint64_t sim_splitmix64_at(uint64_t seed, uint64_t idx) { return splitmix64_at(seed, idx); }
 void sim_gen_points(const uint64_t *k1, const uint64_t *k2, size_t n, uint64_t *g1, uint8_t *g1inf, uint64_t *g2, uint8_t *g2inf) {
-    for (size_t i = 0; i < n; i++) {
-        gen_g1_one(k1[i], g1 + 12 * i, g1inf + i);
-        gen_g2_one(k2[i], g2 + 24 * i, g2inf + i);
-    }
+    run_pair([&]() {
+        for (size_t i = 0; i < n; i++) {
+            gen_g1_one(k1[i], g1 + 12 * i, g1inf + i);
+            gen_g2_one(k2[i], g2 + 24 * i, g2inf + i);
+        }
+    });
 }
-}
-
 #ifdef ZKP_TRACK_BOUNDS
-extern "C" void sim_max_bounds(double *out) {
+void sim_max_bounds(double *out) {
     out[0] = zkp::g_max_lb; out[1] = zkp::g_max_tb; out[2] = zkp::g_max_vb; out[3] = zkp::g_max_col;
 }
 #endif
+}

@@ -88,6 +88,27 @@ static inline void zkp_set_bounds(Fp &r, double lb, double tb, double vb) {
 #define ZKP_SETB(r, lb, tb, vb)
 #endif
 
+// ------------------------------------------------------------------ lane pairing
+//
+// Two adjacent lanes (2k, 2k+1) of a warp cooperate on one pairing: every Fp2 value is split, the
+// even lane holds c0 and the odd lane c1 (tower.cuh).  The only communication is a 14-word
+// shfl.xor with the partner, synchronised on the pair's own two-lane mask so that pairs may
+// diverge from each other (point generation, infinity handling) without deadlock.
+#ifdef ZKP_DEVICE_BUILD
+ZKP_HD int lane_par() { return (int)(threadIdx.x & 1u); }
+ZKP_HD unsigned pair_mask() { return 3u << (threadIdx.x & 30u); }
+ZKP_HD int32_t word_xchg(int32_t v) { return __shfl_xor_sync(pair_mask(), v, 1); }
+#else
+// CPU dev simulation: the two lanes are two host threads in lock-step (tests/host_sim/sim.cpp)
+extern thread_local int zkp_sim_par;
+int32_t zkp_sim_word_xchg(int32_t v);
+void zkp_sim_xchg(void *buf, unsigned long bytes);
+ZKP_HD int lane_par() { return zkp_sim_par; }
+ZKP_HD int32_t word_xchg(int32_t v) { return zkp_sim_word_xchg(v); }
+#endif
+ZKP_HD bool lane_or(bool x) { return (x | (word_xchg(x ? 1 : 0) != 0)); }
+ZKP_HD bool lane_and(bool x) { return (x & (word_xchg(x ? 1 : 0) != 0)); }
+
 // ------------------------------------------------------------------ constants / trivial ops
 ZKP_HD Fp fp_const(const int32_t *k) {   // a normalized constant (Montgomery form), value < p
     Fp r;
@@ -130,6 +151,30 @@ ZKP_HD Fp fp_neg(const Fp &a) {
     return r;
 }
 ZKP_HD Fp fp_dbl(const Fp &a) { return fp_add(a, a); }
+
+// the partner lane's copy of a value
+ZKP_HD Fp fp_xchg(const Fp &a) {
+#ifdef ZKP_DEVICE_BUILD
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < ZKP_NL; i++) r.l[i] = word_xchg(a.l[i]);
+    return r;
+#else
+    Fp r = a;                      // bounds travel with the value in the tracker build
+    zkp_sim_xchg(&r, sizeof(Fp));
+    return r;
+#endif
+}
+// c ? a : b, limb-wise (c is lane-uniform per value, not per limb)
+ZKP_HD Fp fp_select(bool c, const Fp &a, const Fp &b) {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < ZKP_NL; i++) r.l[i] = c ? a.l[i] : b.l[i];
+#ifdef ZKP_TRACK_BOUNDS
+    ZKP_SETB(r, a.lb > b.lb ? a.lb : b.lb, a.tb > b.tb ? a.tb : b.tb, a.vb > b.vb ? a.vb : b.vb);
+#endif
+    return r;
+}
 
 // Weak normalization: one parallel carry round.  l[0..12] end in [-16, 2^28 + 16]; value unchanged.
 ZKP_HD Fp fp_wnorm(const Fp &a) {
@@ -188,6 +233,28 @@ ZKP_HD Fp fp_vreduce(const Fp &a) {
 // a*b/2^392 mod p as a normalized value in (ab/R, ab/R + p).  Separated operand scanning over 27
 // 64-bit column accumulators: 196 IMAD.WIDE for a*b, then per reduction step one IMAD (m) and 14
 // IMAD.WIDE.U32 (m*p); no carries anywhere, the columns are resolved by two shifts each.
+// reduction half shared by the one- and two-product forms: col[0..26] -> normalized limbs
+ZKP_HD Fp mont_reduce(int64_t *col) {
+    int64_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < ZKP_NL; k++) {
+        int64_t t = col[k] + carry;
+        uint32_t m = ((uint32_t)t * ZKP_N0INV) & ZKP_M28;
+        t += (int64_t)((uint64_t)m * (uint32_t)ZKP_P[0]);
+        carry = t >> 28;   // exact: the low 28 bits of t are zero now
+#pragma unroll
+        for (int j = 1; j < ZKP_NL; j++) col[k + j] += (int64_t)((uint64_t)m * (uint32_t)ZKP_P[j]);
+    }
+    Fp r;
+#pragma unroll
+    for (int k = ZKP_NL; k < 2 * ZKP_NL - 1; k++) {
+        int64_t t = col[k] + carry;
+        r.l[k - ZKP_NL] = (int32_t)((uint32_t)t & ZKP_M28);
+        carry = t >> 28;
+    }
+    r.l[ZKP_NL - 1] = (int32_t)carry;
+    return r;
+}
 ZKP_HD Fp mont_mul(const Fp &a, const Fp &b) {
 #ifdef ZKP_TRACK_BOUNDS
     {
@@ -207,27 +274,46 @@ ZKP_HD Fp mont_mul(const Fp &a, const Fp &b) {
         for (int j = 0; j < ZKP_NL - 1; j++) col[i + j] += (int64_t)a.l[i] * (int64_t)b.l[j];
         col[i + ZKP_NL - 1] = (int64_t)a.l[i] * (int64_t)b.l[ZKP_NL - 1];
     }
-    int64_t carry = 0;
-#pragma unroll
-    for (int k = 0; k < ZKP_NL; k++) {
-        int64_t t = col[k] + carry;
-        uint32_t m = ((uint32_t)t * ZKP_N0INV) & ZKP_M28;
-        t += (int64_t)((uint64_t)m * (uint32_t)ZKP_P[0]);
-        carry = t >> 28;   // exact: the low 28 bits of t are zero now
-#pragma unroll
-        for (int j = 1; j < ZKP_NL; j++) col[k + j] += (int64_t)((uint64_t)m * (uint32_t)ZKP_P[j]);
-    }
-    Fp r;
-#pragma unroll
-    for (int k = ZKP_NL; k < 2 * ZKP_NL - 1; k++) {
-        int64_t t = col[k] + carry;
-        r.l[k - ZKP_NL] = (int32_t)((uint32_t)t & ZKP_M28);
-        carry = t >> 28;
-    }
-    r.l[ZKP_NL - 1] = (int32_t)carry;
+    Fp r = mont_reduce(col);
 #ifdef ZKP_TRACK_BOUNDS
     {
         double vb = a.vb * b.vb / ZKP_R_OVER_P + 1.0;
+        ZKP_SETB(r, 268435455.0, vb * ZKP_TOP_PER_P + 2.0, vb);
+    }
+#endif
+    return r;
+}
+// (u*v + w*z)/2^392 mod p with ONE reduction (lazy "sum of products"): 392 + 210 IMADs.  This is
+// one lane's half of an Fp2 product.  Needs 14*(|u||v| + |w||z|) + 2^60 < 2^63.
+ZKP_HD Fp mont_mul2(const Fp &u, const Fp &v, const Fp &w, const Fp &z) {
+#ifdef ZKP_TRACK_BOUNDS
+    {
+        double U = u.lb > u.tb ? u.lb : u.tb, V = v.lb > v.tb ? v.lb : v.tb;
+        double W = w.lb > w.tb ? w.lb : w.tb, Z = z.lb > z.tb ? z.lb : z.tb;
+        double col = 14.0 * (U * V + W * Z) + 14.0 * 72057594037927936.0 + 1099511627776.0;
+        if (col > g_max_col) g_max_col = col;
+        if (col >= 9.2e18) zkp_bound_fail("column accumulator reaches 2^63 in mont_mul2", col);
+        if ((u.vb * v.vb + w.vb * z.vb) / ZKP_R_OVER_P + 1.0 > 2000.0) zkp_bound_fail("product value bound", u.vb * v.vb + w.vb * z.vb);
+    }
+#endif
+    int64_t col[2 * ZKP_NL - 1];
+#pragma unroll
+    for (int j = 0; j < ZKP_NL; j++) col[j] = (int64_t)u.l[0] * (int64_t)v.l[j];
+#pragma unroll
+    for (int i = 1; i < ZKP_NL; i++) {
+#pragma unroll
+        for (int j = 0; j < ZKP_NL - 1; j++) col[i + j] += (int64_t)u.l[i] * (int64_t)v.l[j];
+        col[i + ZKP_NL - 1] = (int64_t)u.l[i] * (int64_t)v.l[ZKP_NL - 1];
+    }
+#pragma unroll
+    for (int i = 0; i < ZKP_NL; i++) {
+#pragma unroll
+        for (int j = 0; j < ZKP_NL; j++) col[i + j] += (int64_t)w.l[i] * (int64_t)z.l[j];
+    }
+    Fp r = mont_reduce(col);
+#ifdef ZKP_TRACK_BOUNDS
+    {
+        double vb = (u.vb * v.vb + w.vb * z.vb) / ZKP_R_OVER_P + 1.0;
         ZKP_SETB(r, 268435455.0, vb * ZKP_TOP_PER_P + 2.0, vb);
     }
 #endif

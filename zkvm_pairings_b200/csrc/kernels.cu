@@ -1,9 +1,9 @@
 // libzkpair.so: CUDA kernels (sm_100a) + the C ABI declared in include/zkpair.h.
 //
-// One thread owns one pairing check (k pairs -> shared-accumulator Miller loop -> final
-// exponentiation); a warp therefore runs 32 independent checks in lock-step (the control flow is
-// data independent), and the integer-multiply pipe is kept busy by the carry-chain Montgomery
-// product in fp.cuh.  Independent checks shard in contiguous slices over the context's devices;
+// A LANE PAIR (two adjacent threads) owns one pairing check (k pairs -> shared-accumulator Miller
+// loop -> final exponentiation): every Fp2 of the tower is split over the pair (tower.cuh), so a
+// warp runs 16 independent checks in lock-step (the control flow is data independent) and the
+// integer-multiply pipe is kept busy by the carry-free 28-bit-limb Montgomery products of fp.cuh.  Independent checks shard in contiguous slices over the context's devices;
 // the only cross-device traffic is the 576-byte Fp12 partial of zkp_multi_miller_product.
 //
 // There is deliberately no CPU implementation in this library: with no CUDA device every entry
@@ -39,35 +39,37 @@ using namespace zkp;
 __global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS)
 k_tower_op(int op, const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, uint64_t *__restrict__ out,
            uint8_t *__restrict__ status, uint32_t *err, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;   // element = lane pair
     if (i >= n) return;
     int na, nb, nr;
     tower_op_shape(op, na, nb, nr);
     uint8_t s = tower_op_one(op, a + (size_t)6 * na * i, nb ? b + (size_t)6 * nb * i : nullptr, out + (size_t)6 * nr * i);
-    if (status) status[i] = s;
-    if ((s & 1) && err) atomicOr(err, 1u);
+    if (lane_par() == 0) {
+        if (status) status[i] = s;
+        if ((s & 1) && err) atomicOr(err, 1u);
+    }
 }
 
-// mode: bit0 Miller loop, bit1 final exponentiation.  One thread per check of k (<= K) pairs.
+// mode: bit0 Miller loop, bit1 final exponentiation.  One lane pair per check of k (<= K) pairs.
 template <int K>
 __global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS)
 k_pairing(int mode, const uint64_t *__restrict__ g1, const uint8_t *__restrict__ g1inf,
           const uint64_t *__restrict__ g2, const uint8_t *__restrict__ g2inf, int k,
           const uint64_t *__restrict__ in12, uint64_t *__restrict__ out, uint8_t *__restrict__ is_one,
           uint32_t *err, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     if (i >= n) return;
     size_t e = i * (size_t)k;
     uint8_t s = pairing_one<K>(mode, g1 ? g1 + 12 * e : nullptr, g1inf ? g1inf + e : nullptr,
                                g2 ? g2 + 24 * e : nullptr, g2inf ? g2inf + e : nullptr, k,
                                in12 ? in12 + 72 * i : nullptr, out + 72 * i, is_one ? is_one + i : nullptr);
-    if (s && err) atomicOr(err, 1u);
+    if (s && err && lane_par() == 0) atomicOr(err, 1u);
 }
 
 // out[t] = in[t] * in[t+m] * in[t+2m] * ...   (t < m <= n), canonical limbs in and out
 __global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS)
 k_fp12_product(const uint64_t *__restrict__ in, size_t n, uint64_t *__restrict__ out, size_t m, uint32_t *err) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     if (t >= m) return;
     bool bad = false;
     Fp12 acc, x;
@@ -77,13 +79,13 @@ k_fp12_product(const uint64_t *__restrict__ in, size_t n, uint64_t *__restrict__
         fp12_mul(acc, acc, x);
     }
     store_fp12(out + 72 * t, acc);
-    if (bad && err) atomicOr(err, 1u);
+    if (lane_or(bad) && err && lane_par() == 0) atomicOr(err, 1u);
 }
 
 __global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS)
 k_gen_points(uint64_t seed, uint64_t first, size_t n, uint64_t *__restrict__ g1, uint8_t *__restrict__ g1inf,
              uint64_t *__restrict__ g2, uint8_t *__restrict__ g2inf) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     if (i >= n) return;
     uint64_t a = splitmix64_at(seed, 2 * (first + i));
     uint64_t b = splitmix64_at(seed, 2 * (first + i) + 1);
@@ -192,7 +194,8 @@ struct zkp_ctx {
     bool timing = false;
 };
 
-static inline unsigned grid_for(size_t n) { return (unsigned)((n + ZKP_TPB - 1) / ZKP_TPB); }
+// two threads (one lane pair) per element
+static inline unsigned grid_for(size_t n) { return (unsigned)((2 * n + ZKP_TPB - 1) / ZKP_TPB); }
 
 static int pair_capacity(int k) { return k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : 8; }
 

@@ -1,6 +1,9 @@
 // Boundary marshalling + per-element operation bodies shared by the CUDA kernels (kernels.cu) and
 // the CPU dev-simulation used by the not-gpu tests (tests/host_sim/sim.cpp).
 //
+// Every routine here is executed by a LANE PAIR (two adjacent threads, tower.cuh): both lanes make
+// the same calls; Fp2-typed data is split between them, Fp-typed data is replicated.
+//
 // Boundary layout (host and device buffers): canonical little-endian u64 limbs, array-of-structs,
 // exactly `Fp.0` of the reference (/root/reference/src/fp.rs:24): Fp = 6 u64, Fp2 = (c0,c1),
 // Fp6 = (c0,c1,c2), Fp12 = (c0,c1) = 72 u64; G1 = x|y, G2 = x.c0|x.c1|y.c0|y.c1.
@@ -58,33 +61,43 @@ ZKP_NOINLINE uint32_t store_fp(uint64_t *dst, Fp m, uint32_t *low) {
     if (low) *low = w[0];
     return rest;
 }
-ZKP_HD void load_fps(Fp *dst, const uint64_t *src, int n, bool &bad) {
-    for (int i = 0; i < n; i++) dst[i] = load_fp(src + 6 * i, bad);
+// Lane-split marshalling: an Fp2 occupies 12 u64 (c0 | c1); the even lane moves c0, the odd lane c1.
+ZKP_HD Fp2 load_fp2(const uint64_t *src, bool &bad) { Fp2 r; r.c = load_fp(src + 6 * lane_par(), bad); return r; }
+ZKP_HD uint32_t store_fp2(uint64_t *dst, const Fp2 &a, uint32_t *low) { return store_fp(dst + 6 * lane_par(), a.c, low); }
+ZKP_HD void load_fp2s(Fp2 *dst, const uint64_t *src, int n, bool &bad) {
+    for (int i = 0; i < n; i++) dst[i] = load_fp2(src + 12 * i, bad);
 }
-ZKP_HD void store_fps(uint64_t *dst, const Fp *src, int n) {
-    for (int i = 0; i < n; i++) store_fp(dst + 6 * i, src[i], nullptr);
+ZKP_HD void store_fp2s(uint64_t *dst, const Fp2 *src, int n) {
+    for (int i = 0; i < n; i++) store_fp2(dst + 12 * i, src[i], nullptr);
 }
 
-// One element of a batched tower op.  a/b/out point at this element's limbs.  Returns a status
-// byte: bit0 = non-canonical input, bit1 = inverse of zero requested (result is zero).
+// One element of a batched tower op, executed by a lane pair.  a/b/out point at this element's
+// limbs.  Returns a status byte (identical in both lanes): bit0 = non-canonical input, bit1 =
+// inverse of zero requested (result is zero).
 ZKP_HD uint8_t tower_op_one(int op, const uint64_t *a, const uint64_t *b, uint64_t *out) {
     int na, nb, nr;
     tower_op_shape(op, na, nb, nr);
     bool bad = false, noinv = false;
-    // operands live in one Fp12-sized union-like buffer set (kept simple: arrays of Fp)
+    if (op < 16) {   // Fp-level: both lanes compute the same value, the even lane stores it
+        Fp x = load_fp(a, bad), y = fp_zero(), r = fp_zero();
+        if (nb) y = load_fp(b, bad);
+        switch (op) {
+            case OP_FP_ADD: r = fp_add(x, y); break;
+            case OP_FP_SUB: r = fp_sub(x, y); break;
+            case OP_FP_NEG: r = fp_neg(x); break;
+            case OP_FP_MUL: r = fmul(x, y); break;
+            case OP_FP_SQR: r = fsqr(x); break;
+            case OP_FP_INV: noinv = fp_is_zero(x); r = fp_inv(x); break;
+            default: bad = true; break;
+        }
+        if (lane_par() == 0) store_fp(out, r, nullptr);
+        return (uint8_t)((bad ? 1 : 0) | (noinv ? 2 : 0));
+    }
     Fp12 A, B, R;
-    Fp *pa = &A.c0.c0.c0, *pb = &B.c0.c0.c0, *pr = &R.c0.c0.c0;
-    load_fps(pa, a, na, bad);
-    if (nb) load_fps(pb, b, nb, bad);
-    const Fp2 *a2 = &A.c0.c0, *b2 = &B.c0.c0;
-    Fp2 *r2 = &R.c0.c0;
+    Fp2 *a2 = &A.c0.c0, *b2 = &B.c0.c0, *r2 = &R.c0.c0;
+    load_fp2s(a2, a, na / 2, bad);
+    if (nb) load_fp2s(b2, b, nb / 2, bad);
     switch (op) {
-        case OP_FP_ADD: pr[0] = fp_add(pa[0], pb[0]); break;
-        case OP_FP_SUB: pr[0] = fp_sub(pa[0], pb[0]); break;
-        case OP_FP_NEG: pr[0] = fp_neg(pa[0]); break;
-        case OP_FP_MUL: pr[0] = fmul(pa[0], pb[0]); break;
-        case OP_FP_SQR: pr[0] = fsqr(pa[0]); break;
-        case OP_FP_INV: noinv = fp_is_zero(pa[0]); pr[0] = fp_inv(pa[0]); break;
         case OP_FP2_ADD: r2[0] = fp2_add(a2[0], b2[0]); break;
         case OP_FP2_SUB: r2[0] = fp2_sub(a2[0], b2[0]); break;
         case OP_FP2_NEG: r2[0] = fp2_neg(a2[0]); break;
@@ -113,7 +126,7 @@ ZKP_HD uint8_t tower_op_one(int op, const uint64_t *a, const uint64_t *b, uint64
         case OP_FP12_SQR: fp12_sqr(R, A); break;
         case OP_FP12_INV: {
             bool z = true;
-            for (int i = 0; i < 12; i++) z = z & fp_is_zero(pa[i]);
+            for (int i = 0; i < 6; i++) z = z & fp2_is_zero(a2[i]);
             noinv = z;
             fp12_inv(R, A);
         } break;
@@ -126,29 +139,27 @@ ZKP_HD uint8_t tower_op_one(int op, const uint64_t *a, const uint64_t *b, uint64
         case OP_FP12_CYC_EXP: cyclotomic_exp(R, A); break;
         default: bad = true; nr = 0; break;
     }
-    store_fps(out, pr, nr);
+    store_fp2s(out, r2, nr / 2);
+    bad = lane_or(bad);
     return (uint8_t)((bad ? 1 : 0) | (noinv ? 2 : 0));
 }
 
 ZKP_HD void load_g1(G1A &p, const uint64_t *xy, bool &bad) { p.x = load_fp(xy, bad); p.y = load_fp(xy + 6, bad); }
-ZKP_HD void load_g2(G2A &q, const uint64_t *xy, bool &bad) {
-    q.x.c0 = load_fp(xy, bad); q.x.c1 = load_fp(xy + 6, bad);
-    q.y.c0 = load_fp(xy + 12, bad); q.y.c1 = load_fp(xy + 18, bad);
-}
-// stores f and returns true when it equals Fp12::one() (canonical 1, 0, ..., 0)
+ZKP_HD void load_g2(G2A &q, const uint64_t *xy, bool &bad) { q.x = load_fp2(xy, bad); q.y = load_fp2(xy + 12, bad); }
+// stores f and returns true (in both lanes) when it equals Fp12::one() (canonical 1, 0, ..., 0)
 ZKP_HD bool store_fp12(uint64_t *dst, const Fp12 &f) {
-    const Fp *c = &f.c0.c0.c0;
+    const Fp2 *c = &f.c0.c0;
     uint32_t low = 0, rest = 0;
-    rest |= store_fp(dst, c[0], &low);
-    bool one = (low == 1u);
-    for (int i = 1; i < 12; i++) {
+    rest |= store_fp2(dst, c[0], &low);
+    bool first = lane_par() == 0 ? (low == 1u) : (low == 0u);
+    for (int i = 1; i < 6; i++) {
         uint32_t l2 = 0;
-        rest |= store_fp(dst + 6 * i, c[i], &l2);
+        rest |= store_fp2(dst + 12 * i, c[i], &l2);
         rest |= l2;
     }
-    return one & (rest == 0);
+    return lane_and(first & (rest == 0));
 }
-ZKP_HD void load_fp12(Fp12 &f, const uint64_t *src, bool &bad) { load_fps(&f.c0.c0.c0, src, 12, bad); }
+ZKP_HD void load_fp12(Fp12 &f, const uint64_t *src, bool &bad) { load_fp2s(&f.c0.c0, src, 6, bad); }
 
 // mode bits for pairing_one
 enum { ZKP_DO_MILLER = 1, ZKP_DO_FINAL_EXP = 2 };
@@ -178,8 +189,8 @@ ZKP_HD uint8_t pairing_one(int mode, const uint64_t *g1, const uint8_t *g1inf, c
     }
     if (mode & ZKP_DO_FINAL_EXP) final_exponentiation(f, f);
     bool one = store_fp12(out, f);
-    if (is_one) *is_one = one ? 1 : 0;
-    return bad ? 1 : 0;
+    if (is_one && lane_par() == 0) *is_one = one ? 1 : 0;
+    return lane_or(bad) ? 1 : 0;
 }
 
 // SplitMix64 output number idx+1 of the stream seeded with `seed` (random access)
@@ -193,17 +204,20 @@ ZKP_HD uint64_t splitmix64_at(uint64_t seed, uint64_t idx) {
 // [k]G for the G1 / G2 generators, k = 64-bit scalar (synthetic input generation, untimed)
 ZKP_HD void gen_g1_one(uint64_t k, uint64_t *xy, uint8_t *inf) {
     Fp gx = fp_const(ZKP_G1_GEN), gy = fp_const(ZKP_G1_GEN + ZKP_NL), ax, ay;
-    *inf = scalar_mul_affine<OpsFp>(ax, ay, gx, gy, &k, 64) ? 1 : 0;
-    store_fp(xy, ax, nullptr);
-    store_fp(xy + 6, ay, nullptr);
+    bool is_inf = scalar_mul_affine<OpsFp>(ax, ay, gx, gy, &k, 64);   // both lanes hold the same point
+    if (lane_par() == 0) {
+        *inf = is_inf ? 1 : 0;
+        store_fp(xy, ax, nullptr);
+    } else {
+        store_fp(xy + 6, ay, nullptr);
+    }
 }
 ZKP_HD void gen_g2_one(uint64_t k, uint64_t *xy, uint8_t *inf) {
-    Fp2 gx, gy, ax, ay;
-    gx.c0 = fp_const(ZKP_G2_GEN); gx.c1 = fp_const(ZKP_G2_GEN + ZKP_NL);
-    gy.c0 = fp_const(ZKP_G2_GEN + 2 * ZKP_NL); gy.c1 = fp_const(ZKP_G2_GEN + 3 * ZKP_NL);
-    *inf = scalar_mul_affine<OpsFp2>(ax, ay, gx, gy, &k, 64) ? 1 : 0;
-    store_fp(xy, ax.c0, nullptr); store_fp(xy + 6, ax.c1, nullptr);
-    store_fp(xy + 12, ay.c0, nullptr); store_fp(xy + 18, ay.c1, nullptr);
+    Fp2 gx = fp2_const(ZKP_G2_GEN), gy = fp2_const(ZKP_G2_GEN + 2 * ZKP_NL), ax, ay;
+    bool is_inf = scalar_mul_affine<OpsFp2>(ax, ay, gx, gy, &k, 64);
+    if (lane_par() == 0) *inf = is_inf ? 1 : 0;
+    store_fp2(xy, ax, nullptr);
+    store_fp2(xy + 12, ay, nullptr);
 }
 
 }  // namespace zkp

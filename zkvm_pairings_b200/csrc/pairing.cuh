@@ -10,8 +10,8 @@
 
 namespace zkp {
 
-struct G1A { Fp x, y; };          // affine G1 (src/g1.rs:7-11), Montgomery coordinates
-struct G2A { Fp2 x, y; };         // affine G2 (src/g2.rs:8-12)
+struct G1A { Fp x, y; };          // affine G1 (src/g1.rs:7-11), Montgomery coordinates, same in both lanes
+struct G2A { Fp2 x, y; };         // affine G2 (src/g2.rs:8-12), lane-split like every Fp2
 struct G2P { Fp2 x, y, z; };      // Jacobian-style projective G2 used by the line steps
 
 // SURVEY 9.1 doubling_step: 8 Fp2 sqr + 3 Fp2 mul.  co = (c0, c1, c2).  r stays normalized.

@@ -6,11 +6,15 @@
 // Fp6 mul = 6 Fp2 mul, Fp12 mul = 3 Fp6 mul) instead of the reference's schoolbook Fp2
 // (src/fp2.rs:192-209) and 36-mul interleaved Fp6 (src/fp6.rs:188-267).
 //
-// Code-size / register strategy: the 420-IMAD Montgomery product is ONE out-of-line function
-// (fmul) whose operands and result travel in registers (28 in, 14 out -- verified in SASS: no
-// stack traffic), so its body stays hot in the instruction cache and every call site is a few
-// dozen instructions.  Fp/Fp2 additions are inlined (14 carry-free adds per Fp); Fp6-level and
-// larger operations are out-of-line and exchange operands through thread-local memory.
+// Work split: TWO lanes per pairing.  Every Fp2 is split over an even/odd lane pair (see the Fp2
+// section), so a thread carries half of the tower state (an Fp12 is 6 x 14 registers per lane)
+// and the Fp6-level working sets fit the register file.
+//
+// Code-size / register strategy: the Fp2 product and square (602 / 420 IMADs per lane) are
+// out-of-line functions whose operands and result travel in registers (28 in, 14 out), so their
+// bodies stay hot in the instruction cache.  Additions are inlined (14 carry-free adds per lane);
+// Fp6-level and larger operations are out-of-line and exchange operands through thread-local
+// memory.
 //
 // Lazy reduction: additions never reduce; products come back normalized.  Every Fp2
 // product/square weakly normalizes its outputs (fp_wnorm, one parallel carry round) so limb
@@ -40,49 +44,69 @@ ZKP_NOINLINE Fp fp_inv(Fp a) {
     return res;
 }
 
-// ------------------------------------------------------------------ Fp2
+// ------------------------------------------------------------------ Fp2 (split over a lane pair)
+//
+// An Fp2 value a0 + a1*u lives in TWO adjacent lanes: the even lane holds a0, the odd lane a1.
+// Additions are lane-local; a product costs each lane one exchange (2 x 14 shfl.xor) and one lazy
+// "two products, one reduction" (fp.cuh mont_mul2):
+//     even lane:  c0 = a0*b0 - a1*b1            odd lane:  c1 = a0*b1 + a1*b0
+// i.e. the schoolbook form of src/fp2.rs:192-209, which with a single reduction per lane costs
+// 2*(392+210) = 1204 IMADs per Fp2 product against 3*420 = 1260 for Karatsuba over full Fp
+// products -- and both lanes do identical work, so there is no divergence and no idle lane.
 struct Fp2 {
-    Fp c0, c1;
+    Fp c;   // c0 in even lanes, c1 in odd lanes
 };
 
-ZKP_HD Fp2 fp2_zero() { Fp2 r; r.c0 = fp_zero(); r.c1 = fp_zero(); return r; }
-ZKP_HD Fp2 fp2_one() { Fp2 r; r.c0 = fp_one(); r.c1 = fp_zero(); return r; }
-ZKP_HD bool fp2_is_zero(const Fp2 &a) { return fp_is_zero(a.c0) & fp_is_zero(a.c1); }
-ZKP_HD Fp2 fp2_vreduce(const Fp2 &a) { Fp2 r; r.c0 = fp_vreduce(a.c0); r.c1 = fp_vreduce(a.c1); return r; }
-ZKP_HD Fp2 fp2_wnorm(const Fp2 &a) { Fp2 r; r.c0 = fp_wnorm(a.c0); r.c1 = fp_wnorm(a.c1); return r; }
-ZKP_HD Fp2 fp2_add(const Fp2 &a, const Fp2 &b) { Fp2 r; r.c0 = fp_add(a.c0, b.c0); r.c1 = fp_add(a.c1, b.c1); return r; }   // src/fp2.rs:216-218
-ZKP_HD Fp2 fp2_sub(const Fp2 &a, const Fp2 &b) { Fp2 r; r.c0 = fp_sub(a.c0, b.c0); r.c1 = fp_sub(a.c1, b.c1); return r; }   // src/fp2.rs:221-223
-ZKP_HD Fp2 fp2_neg(const Fp2 &a) { Fp2 r; r.c0 = fp_neg(a.c0); r.c1 = fp_neg(a.c1); return r; }                            // src/fp2.rs:226-228
+ZKP_HD Fp2 fp2_zero() { Fp2 r; r.c = fp_zero(); return r; }
+ZKP_HD Fp2 fp2_one() { Fp2 r; r.c = fp_select(lane_par() != 0, fp_zero(), fp_one()); return r; }
+// constant stored as c0 | c1 (2 x 14 limbs, Montgomery form)
+ZKP_HD Fp2 fp2_const(const int32_t *k) { Fp2 r; r.c = fp_const(k + lane_par() * ZKP_NL); return r; }
+ZKP_HD bool fp2_is_zero(const Fp2 &a) { return lane_and(fp_is_zero(a.c)); }
+ZKP_HD Fp2 fp2_vreduce(const Fp2 &a) { Fp2 r; r.c = fp_vreduce(a.c); return r; }
+ZKP_HD Fp2 fp2_wnorm(const Fp2 &a) { Fp2 r; r.c = fp_wnorm(a.c); return r; }
+ZKP_HD Fp2 fp2_add(const Fp2 &a, const Fp2 &b) { Fp2 r; r.c = fp_add(a.c, b.c); return r; }   // src/fp2.rs:216-218
+ZKP_HD Fp2 fp2_sub(const Fp2 &a, const Fp2 &b) { Fp2 r; r.c = fp_sub(a.c, b.c); return r; }   // src/fp2.rs:221-223
+ZKP_HD Fp2 fp2_neg(const Fp2 &a) { Fp2 r; r.c = fp_neg(a.c); return r; }                      // src/fp2.rs:226-228
 ZKP_HD Fp2 fp2_dbl(const Fp2 &a) { return fp2_add(a, a); }
-ZKP_HD Fp2 fp2_conj(const Fp2 &a) { Fp2 r; r.c0 = a.c0; r.c1 = fp_neg(a.c1); return r; }                                  // src/fp2.rs:155-157
+// (a0, -a1)   -- src/fp2.rs:155-157
+ZKP_HD Fp2 fp2_conj(const Fp2 &a) { Fp2 r; r.c = fp_select(lane_par() != 0, fp_neg(a.c), a.c); return r; }
 // (a + bu)(1 + u) = (a - b) + (a + b)u   -- src/fp2.rs:161-168
-ZKP_HD Fp2 fp2_mul_nr(const Fp2 &a) { Fp2 r; r.c0 = fp_sub(a.c0, a.c1); r.c1 = fp_add(a.c0, a.c1); return r; }
-// Karatsuba, 3 Fp mul (value-equal to the schoolbook src/fp2.rs:192-209).  Both operands must be
-// (weakly) normalized: the middle product multiplies two sums of two limbs, 14*(2N)*(2N) < 2^63.
-// Output weakly normalized.
-ZKP_HD Fp2 fp2_mul(const Fp2 &a, const Fp2 &b) {
-    Fp t0 = fmul(a.c0, b.c0);
-    Fp t1 = fmul(a.c1, b.c1);
-    Fp s = fmul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
+ZKP_HD Fp2 fp2_mul_nr(const Fp2 &a) {
+    Fp t = fp_xchg(a.c);
     Fp2 r;
-    r.c0 = fp_wnorm(fp_sub(t0, t1));
-    r.c1 = fp_wnorm(fp_sub(fp_sub(s, t0), t1));
+    r.c = fp_add(a.c, fp_select(lane_par() != 0, t, fp_neg(t)));
     return r;
 }
-// complex squaring, 2 Fp mul  -- src/fp2.rs:171-189 ; products come back normalized
-ZKP_HD Fp2 fp2_sqr(const Fp2 &a) {
+// Product.  Operand limb bounds La, Lb need 28*La*Lb + 2^60 < 2^63: each operand may be a sum of
+// two normalized values.  The result is a normalized product.
+ZKP_NOINLINE Fp2 fp2_mul(Fp2 a, Fp2 b) {
+    bool odd = lane_par() != 0;
+    Fp pa = fp_xchg(a.c), pb = fp_xchg(b.c);
+    Fp u = fp_select(odd, pa, a.c);            // a0
+    Fp w = fp_select(odd, a.c, fp_neg(pa));    // even: -a1   odd: a1
     Fp2 r;
-    r.c0 = fmul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1));
-    r.c1 = fmul(fp_dbl(a.c0), a.c1);
+    r.c = mont_mul2(u, b.c, w, pb);            // even: a0*b0 - a1*b1   odd: a0*b1 + a1*b0
     return r;
 }
-ZKP_HD Fp2 fp2_mul_fp(const Fp2 &a, const Fp &k) { Fp2 r; r.c0 = fmul(a.c0, k); r.c1 = fmul(a.c1, k); return r; }   // src/fp2.rs:95-102
-// src/fp2.rs:278-296 ; zero maps to zero
+// Square (complex method, src/fp2.rs:171-189): even lane (a0+a1)(a0-a1), odd lane (2 a0) a1.
+// The operand must be (weakly) normalized.
+ZKP_NOINLINE Fp2 fp2_sqr(Fp2 a) {
+    bool odd = lane_par() != 0;
+    Fp pa = fp_xchg(a.c);
+    Fp x = fp_add(pa, fp_select(odd, pa, a.c));
+    Fp y = fp_select(odd, a.c, fp_sub(a.c, pa));
+    Fp2 r;
+    r.c = mont_mul(x, y);
+    return r;
+}
+ZKP_HD Fp2 fp2_mul_fp(const Fp2 &a, const Fp &k) { Fp2 r; r.c = fmul(a.c, k); return r; }   // src/fp2.rs:95-102
+// src/fp2.rs:278-296 ; zero maps to zero.  Both lanes run the Fermat inversion of the norm.
 ZKP_HD Fp2 fp2_inv(const Fp2 &a) {
-    Fp t = fp_inv(fp_add(fsqr(a.c0), fsqr(a.c1)));
+    Fp n = fsqr(a.c);
+    Fp t = fp_inv(fp_add(n, fp_xchg(n)));
+    Fp m = fmul(a.c, t);
     Fp2 r;
-    r.c0 = fmul(a.c0, t);
-    r.c1 = fp_neg(fmul(a.c1, t));
+    r.c = fp_select(lane_par() != 0, fp_neg(m), m);
     return r;
 }
 
@@ -162,7 +186,7 @@ struct Fp12 {
     Fp6 c0, c1;
 };
 
-ZKP_HD void fp12_set_one(Fp12 &r) { fp6_set_zero(r.c0); fp6_set_zero(r.c1); r.c0.c0.c0 = fp_one(); }
+ZKP_HD void fp12_set_one(Fp12 &r) { fp6_set_zero(r.c0); fp6_set_zero(r.c1); r.c0.c0 = fp2_one(); }
 ZKP_HD void fp12_conj(Fp12 &r, const Fp12 &a) { r.c0 = a.c0; fp6_neg(r.c1, a.c1); }   // src/fp12.rs:123-125
 // Karatsuba over Fp6, 3 Fp6 mul  -- src/fp12.rs:193-210 ; r may alias a or b
 ZKP_NOINLINE void fp12_mul(Fp12 &r, const Fp12 &a, const Fp12 &b) {
@@ -240,10 +264,7 @@ ZKP_NOINLINE void fp12_frobenius(Fp12 &r, const Fp12 &a, int k) {
         Fp2 c = *src[i];
         if (k & 1) c = fp2_conj(c);
         if (i > 0) {
-            Fp2 g;
-            g.c0 = fp_const(tab + (i - 1) * 2 * ZKP_NL);
-            g.c1 = fp_const(tab + (i - 1) * 2 * ZKP_NL + ZKP_NL);
-            c = fp2_mul(c, g);
+            c = fp2_mul(c, fp2_const(tab + (i - 1) * 2 * ZKP_NL));
         }
         *dst[i] = c;
     }
