@@ -233,17 +233,27 @@ ZKP_HD Fp fp_vreduce(const Fp &a) {
 // a*b/2^392 mod p as a normalized value in (ab/R, ab/R + p).  Separated operand scanning over 27
 // 64-bit column accumulators: 196 IMAD.WIDE for a*b, then per reduction step one IMAD (m) and 14
 // IMAD.WIDE.U32 (m*p); no carries anywhere, the columns are resolved by two shifts each.
+// m = (t * n0') mod 2^28 as a plain 32-bit value.  The opaque move keeps the compiler from
+// re-deriving the multiplier as a masked 64-bit quantity (it then emits 64-bit multiplies whose
+// zero high halves survive as an extra add after every IMAD.WIDE).
+ZKP_HD int32_t mont_m(uint32_t t_lo) {
+    int32_t m = (int32_t)((t_lo * ZKP_N0INV) & ZKP_M28);
+#ifdef ZKP_DEVICE_BUILD
+    asm("" : "+r"(m));
+#endif
+    return m;
+}
 // reduction half shared by the one- and two-product forms: col[0..26] -> normalized limbs
 ZKP_HD Fp mont_reduce(int64_t *col) {
     int64_t carry = 0;
 #pragma unroll
     for (int k = 0; k < ZKP_NL; k++) {
         int64_t t = col[k] + carry;
-        uint32_t m = ((uint32_t)t * ZKP_N0INV) & ZKP_M28;
-        t += (int64_t)((uint64_t)m * (uint32_t)ZKP_P[0]);
+        int32_t m = mont_m((uint32_t)t);
+        t += (int64_t)m * (int64_t)ZKP_P[0];
         carry = t >> 28;   // exact: the low 28 bits of t are zero now
 #pragma unroll
-        for (int j = 1; j < ZKP_NL; j++) col[k + j] += (int64_t)((uint64_t)m * (uint32_t)ZKP_P[j]);
+        for (int j = 1; j < ZKP_NL; j++) col[k + j] += (int64_t)m * (int64_t)ZKP_P[j];
     }
     Fp r;
 #pragma unroll
