@@ -1,9 +1,9 @@
 // DEV SIMULATION of the device code for the CPU ("not gpu") test-suite.
 //
 // Compiles the very same headers the CUDA kernels are built from (zkvm_pairings_b200/csrc/*.cuh)
-// as plain C++, so the limb-level Montgomery arithmetic, the lazy-reduction bounds
-// (-DZKP_TRACK_BOUNDS), the tower and the pairing control flow can be checked against the oracle
-// without a GPU.  The two lanes that share one pairing on the device are two host threads in
+// as plain C++ (the PTX carry flag emulated), so the limb-level Montgomery arithmetic, its operand
+// bounds (ZKP_SIM_ASSERT aborts on a violation), the tower and the pairing control flow can be
+// checked against the oracle without a GPU.  The two lanes that share one pairing on the device are two host threads in
 // lock-step here; the shfl.xor exchange is a two-party rendezvous.  TEST INFRASTRUCTURE ONLY: built
 // into tests/host_sim/libzkpair_sim*.so, never linked into or loaded by libzkpair.so / the
 // zkvm_pairings_b200 package, and not a CPU fallback (the product path raises when the CUDA
@@ -39,7 +39,7 @@ void zkp_sim_xchg(void *buf, unsigned long bytes) {
     memcpy(buf, g_slot[zkp_sim_par ^ 1], bytes);
     pair_barrier();
 }
-int32_t zkp_sim_word_xchg(int32_t v) {
+uint32_t zkp_sim_word_xchg(uint32_t v) {
     zkp_sim_xchg(&v, sizeof v);
     return v;
 }
@@ -94,9 +94,4 @@ void sim_gen_points(const uint64_t *k1, const uint64_t *k2, size_t n, uint64_t *
         }
     });
 }
-#ifdef ZKP_TRACK_BOUNDS
-void sim_max_bounds(double *out) {
-    out[0] = zkp::g_max_lb; out[1] = zkp::g_max_tb; out[2] = zkp::g_max_vb; out[3] = zkp::g_max_col;
-}
-#endif
 }

@@ -1,29 +1,34 @@
-// Fp: BLS12-381 base field on sm_100a -- 14 signed limbs of 28 bits, Montgomery form R = 2^392.
+// Fp: BLS12-381 base field on sm_100a -- 12 saturated 32-bit limbs, Montgomery form R = 2^384.
 //
 // Replaces the reference's host Fp arithmetic (BigUint mul/add followed by "% p",
 // /root/reference/src/fp.rs:351-368, :415-434) and its zkVM precompile calls
 // (bls12381_sys_bigint / syscall_bls12381_fp_mulmod, src/fp.rs:126,376,443).  Values cross the
 // boundary as canonical little-endian limbs (src/fp.rs:24) and are converted at load/store.
 //
-// Why 14 x 28 bits and not 12 x 32 (the v0 design): on B200 a plain IMAD.WIDE issues at the full
-// fmaheavy rate (measured 18.2 T/s) but the carry-chained IMAD.WIDE.U32.X that saturated 32-bit
-// limbs need issues at HALF of it (9.1 T/s; profiles/r1a_v0_saturated_cios_ncu_summary.txt).
-// With 28-bit limbs every 32x32->64 product has 8 spare bits, so whole columns of partial products
-// accumulate in 64-bit registers with NO carries: a Montgomery product is 14*14 (a*b) + 14*14
-// (m*p) + 14 (m = t*n0') = 420 full-rate IMADs with 14-way instruction-level parallelism, against
-// 300 half-rate ones before.  Additions and subtractions become 14 independent 32-bit adds (no
-// carry chain, no conditional subtraction): limbs are SIGNED and values are kept lazily reduced.
+// Cost model (measured on B200, tools/imad_probe.cu): every 32x32->64 multiply-accumulate
+// (IMAD.WIDE.U32, with or without carry in/out) occupies the fmaheavy pipe for 4 cycles per warp
+// and is THE scarce resource; IADD3/LOP3/SEL run on the separate ALU pipe.  So the design
+// minimises wide MACs and lets additions cost what they cost:
+//   * saturated 32-bit limbs: 12 x 12 = 144 MACs per product, 12 x 13 = 156 per Montgomery
+//     reduction (the 14 x 28-bit carry-free layout tried in between needs 196 / 210);
+//   * rows are carry chains of mad.lo.cc / madc.hi.cc pairs, which ptxas fuses into one
+//     IMAD.WIDE.U32(.X) each; partial products live in two interleaved accumulators ("even" =
+//     64-bit aligned columns, "odd" = columns offset by 32 bits), so every MAC lands on a
+//     register pair and the even/odd chains of a row are independent;
+//   * "two products, one reduction": mont_mul2 computes (u*v + w*z)/R with 288 + 156 MACs -- one
+//     lane's half of an Fp2 product (tower.cuh) -- instead of 2 x 300.
 //
-// Representation invariants (checked statically by the bound tracker, see ZKP_TRACK_BOUNDS):
-//   * value  v = sum l[i] * 2^(28 i), congruent to (x * 2^392) mod p, |v| < 2^11 * p;
-//   * "normalized": l[0..12] in [0, 2^28), l[13] small and signed (it carries the sign of v);
-//   * add/sub/neg are limb-wise and only grow the limb bound; fp_wnorm() brings l[0..12] back to
-//     [-16, 2^28 + 16] in one parallel round;
-//   * fp_mul needs  14 * max|a.l| * max|b.l| + 2^60 < 2^63  and returns a normalized value in
-//     (ab/R, ab/R + p), i.e. within (-0.1p, 1.1p) for operands below 16p.
+// Representation invariant: every Fp that leaves a function of this file is a value in [0, 2p]
+// congruent to x * 2^384 mod p ("2p-redundant"): add/sub correct by +-2p with one conditional
+// step and never produce canonical values; only the boundary (fp_to_words) reduces to [0, p).
+// Montgomery bound: for T = u*v (+ w*z) < p * 2^384 the result (T + m*p)/R lies in [0, 2p).
+// With all operands <= 2p, T <= 8 p^2 < 0.82 * p * 2^384 (p < 2^381: three spare bits).  The
+// squaring passes one lazily added operand (<= 4p) together with a corrected one (<= 2p): same
+// bound.  The CPU dev simulation (tests/host_sim/sim.cpp) asserts these operand bounds on every
+// call (ZKP_SIM_ASSERT); they depend on the call sites, not on the data.
 //
-// The header is plain C++ (no PTX), so the identical code is exercised on the CPU by the dev
-// simulation tests/host_sim/sim.cpp (never linked into libzkpair.so).
+// The header is plain C++ plus ten PTX carry primitives that have a host emulation, so the
+// identical code is exercised on the CPU by the dev simulation (never linked into libzkpair.so).
 #pragma once
 #include <stdint.h>
 
@@ -34,120 +39,154 @@
 #define ZKP_HOSTDEV __host__ __device__ inline
 #define ZKP_NOINLINE __device__ __noinline__
 #define ZKP_CONST __device__ __constant__ const
+#define ZKP_SIM_ASSERT(cond, what)
 #else
+#include <cstdio>
+#include <cstdlib>
 #define ZKP_HD static inline
 #define ZKP_MEMBER inline
 #define ZKP_HOSTDEV static inline
 #define ZKP_NOINLINE static __attribute__((noinline))
 #define ZKP_CONST static const
+#define ZKP_SIM_ASSERT(cond, what)                                                       \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            fprintf(stderr, "ZKP bound violation: %s (%s:%d)\n", what, __FILE__, __LINE__); \
+            abort();                                                                     \
+        }                                                                                \
+    } while (0)
 #endif
 
 #include "consts.cuh"
 
-#ifdef ZKP_TRACK_BOUNDS
-#include <cstdio>
-#include <cstdlib>
-#include <execinfo.h>
-#endif
-
 namespace zkp {
 
-#define ZKP_NL 14
-#define ZKP_M28 0x0fffffff
+#define ZKP_NL 12
 
-struct Fp {
-    int32_t l[ZKP_NL];
-#ifdef ZKP_TRACK_BOUNDS
-    // worst-case bounds carried along in the CPU dev simulation only: |l[0..12]| <= lb,
-    // |l[13]| <= tb, |value| <= vb * p.  They depend on the formula DAG, not on the data.
-    double lb, tb, vb;
-#endif
+struct alignas(16) Fp {
+    uint32_t l[ZKP_NL];
 };
 
-#ifdef ZKP_TRACK_BOUNDS
-#define ZKP_TOP_PER_P 106514.0          /* ceil(p / 2^364) */
-#define ZKP_R_OVER_P 2520.0             /* floor(2^392 / p) */
-static double g_max_lb = 0, g_max_tb = 0, g_max_vb = 0, g_max_col = 0;
-static inline void zkp_bound_fail(const char *what, double v) {
-    fprintf(stderr, "ZKP bound violation: %s (%.4g = 2^%.2f)\n", what, v, __builtin_log2(v));
-    void *bt[32];
-    int n = backtrace(bt, 32);
-    backtrace_symbols_fd(bt, n, 2);
-    abort();
-}
-static inline void zkp_set_bounds(Fp &r, double lb, double tb, double vb) {
-    r.lb = lb; r.tb = tb; r.vb = vb;
-    if (lb > g_max_lb) g_max_lb = lb;
-    if (tb > g_max_tb) g_max_tb = tb;
-    if (vb > g_max_vb) g_max_vb = vb;
-    if (lb >= 2147483000.0) zkp_bound_fail("limb magnitude reaches 2^31", lb);
-    if (tb >= 2147483000.0) zkp_bound_fail("top limb magnitude reaches 2^31", tb);
-}
-#define ZKP_SETB(r, lb, tb, vb) zkp_set_bounds(r, lb, tb, vb)
+// ------------------------------------------------------------------ carry-chain primitives
+#ifdef ZKP_DEVICE_BUILD
+ZKP_HD uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZKP_HD uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZKP_HD uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZKP_HD uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZKP_HD uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZKP_HD uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZKP_HD uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ZKP_HD uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ZKP_HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ZKP_HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 #else
-#define ZKP_SETB(r, lb, tb, vb)
+// host emulation of the PTX condition-code register (one flag per simulated lane = host thread)
+static thread_local uint32_t ZKP_CF = 0;
+ZKP_HD uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b; ZKP_CF = (uint32_t)(s >> 32); return (uint32_t)s; }
+ZKP_HD uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b + ZKP_CF; ZKP_CF = (uint32_t)(s >> 32); return (uint32_t)s; }
+ZKP_HD uint32_t addc(uint32_t a, uint32_t b) { return a + b + ZKP_CF; }
+ZKP_HD uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t d = (uint64_t)a - b; ZKP_CF = (uint32_t)(d >> 63); return (uint32_t)d; }
+ZKP_HD uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t d = (uint64_t)a - b - ZKP_CF; ZKP_CF = (uint32_t)(d >> 63); return (uint32_t)d; }
+ZKP_HD uint32_t subc(uint32_t a, uint32_t b) { return a - b - ZKP_CF; }
+ZKP_HD uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (uint64_t)(uint32_t)(a * b) + c; ZKP_CF = (uint32_t)(s >> 32); return (uint32_t)s; }
+ZKP_HD uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (uint64_t)(uint32_t)(a * b) + c + ZKP_CF; ZKP_CF = (uint32_t)(s >> 32); return (uint32_t)s; }
+ZKP_HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (((uint64_t)a * b) >> 32) + c + ZKP_CF; ZKP_CF = (uint32_t)(s >> 32); return (uint32_t)s; }
+ZKP_HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)(((uint64_t)a * b) >> 32) + c + ZKP_CF; }
 #endif
 
 // ------------------------------------------------------------------ lane pairing
 //
 // Two adjacent lanes (2k, 2k+1) of a warp cooperate on one pairing: every Fp2 value is split, the
-// even lane holds c0 and the odd lane c1 (tower.cuh).  The only communication is a 14-word
+// even lane holds c0 and the odd lane c1 (tower.cuh).  The only communication is a 12-word
 // shfl.xor with the partner, synchronised on the pair's own two-lane mask so that pairs may
 // diverge from each other (point generation, infinity handling) without deadlock.
 #ifdef ZKP_DEVICE_BUILD
 ZKP_HD int lane_par() { return (int)(threadIdx.x & 1u); }
 ZKP_HD unsigned pair_mask() { return 3u << (threadIdx.x & 30u); }
-ZKP_HD int32_t word_xchg(int32_t v) { return __shfl_xor_sync(pair_mask(), v, 1); }
+ZKP_HD uint32_t word_xchg(uint32_t v) { return __shfl_xor_sync(pair_mask(), v, 1); }
 #else
 // CPU dev simulation: the two lanes are two host threads in lock-step (tests/host_sim/sim.cpp)
 extern thread_local int zkp_sim_par;
-int32_t zkp_sim_word_xchg(int32_t v);
+uint32_t zkp_sim_word_xchg(uint32_t v);
 void zkp_sim_xchg(void *buf, unsigned long bytes);
 ZKP_HD int lane_par() { return zkp_sim_par; }
-ZKP_HD int32_t word_xchg(int32_t v) { return zkp_sim_word_xchg(v); }
+ZKP_HD uint32_t word_xchg(uint32_t v) { return zkp_sim_word_xchg(v); }
 #endif
-ZKP_HD bool lane_or(bool x) { return (x | (word_xchg(x ? 1 : 0) != 0)); }
-ZKP_HD bool lane_and(bool x) { return (x & (word_xchg(x ? 1 : 0) != 0)); }
+ZKP_HD bool lane_or(bool x) { return (x | (word_xchg(x ? 1u : 0u) != 0)); }
+ZKP_HD bool lane_and(bool x) { return (x & (word_xchg(x ? 1u : 0u) != 0)); }
 
 // ------------------------------------------------------------------ constants / trivial ops
-ZKP_HD Fp fp_const(const int32_t *k) {   // a normalized constant (Montgomery form), value < p
+ZKP_HD Fp fp_const(const uint32_t *k) {   // a constant in Montgomery form, value < p
     Fp r;
 #pragma unroll
     for (int i = 0; i < ZKP_NL; i++) r.l[i] = k[i];
-    ZKP_SETB(r, 268435456.0, ZKP_TOP_PER_P, 1.0);
     return r;
 }
 ZKP_HD Fp fp_zero() {
     Fp r;
 #pragma unroll
     for (int i = 0; i < ZKP_NL; i++) r.l[i] = 0;
-    ZKP_SETB(r, 0.0, 0.0, 0.0);
     return r;
 }
 ZKP_HD Fp fp_one() { return fp_const(ZKP_ONE); }   // Montgomery one; canonical one is [1,0,..] (src/fp.rs:154-156)
 
-// (a + b), lazily: no carry, no reduction   -- value-equal mod p to src/fp.rs:351-368
-ZKP_HD Fp fp_add(const Fp &a, const Fp &b) {
-    Fp r;
+// a >= k ?  (k = 12 constant words)
+ZKP_HD bool fp_geq_const(const Fp &a, const uint32_t *k) {
+    sub_cc(a.l[0], k[0]);
 #pragma unroll
-    for (int i = 0; i < ZKP_NL; i++) r.l[i] = a.l[i] + b.l[i];
-    ZKP_SETB(r, a.lb + b.lb, a.tb + b.tb, a.vb + b.vb);
+    for (int i = 1; i < ZKP_NL; i++) subc_cc(a.l[i], k[i]);
+    return subc(0, 0) == 0;
+}
+#ifndef ZKP_DEVICE_BUILD
+ZKP_HD bool fp_leq_2p(const Fp &a) { return !fp_geq_const(a, ZKP_2P1); }   // dev-simulation bound checks
+ZKP_HD bool fp_leq_4p(const Fp &a) { return !fp_geq_const(a, ZKP_4P1); }
+#endif
+
+// plain 384-bit sum, no correction: the caller guarantees a + b < 2^384 and a consumer that
+// accepts the larger value (one operand of a single-product mont_mul)
+ZKP_HD Fp fp_add_lazy(const Fp &a, const Fp &b) {
+    Fp r;
+    r.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < ZKP_NL - 1; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+    r.l[ZKP_NL - 1] = addc(a.l[ZKP_NL - 1], b.l[ZKP_NL - 1]);
     return r;
 }
-// (a - b), lazily (limbs are signed)        -- src/fp.rs:407-411
+// a in [0, 4p] -> [0, 2p]: subtract 2p when that does not go negative
+ZKP_HD Fp fp_correct(const Fp &s) {
+    Fp t;
+    t.l[0] = sub_cc(s.l[0], ZKP_2P[0]);
+#pragma unroll
+    for (int i = 1; i < ZKP_NL; i++) t.l[i] = subc_cc(s.l[i], ZKP_2P[i]);
+    bool neg = subc(0, 0) != 0;
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < ZKP_NL; i++) r.l[i] = neg ? s.l[i] : t.l[i];
+    return r;
+}
+// (a + b) mod p, 2p-redundant   -- value-equal mod p to src/fp.rs:351-368
+ZKP_HD Fp fp_add(const Fp &a, const Fp &b) { return fp_correct(fp_add_lazy(a, b)); }
+// (a - b) mod p, 2p-redundant   -- src/fp.rs:407-411
 ZKP_HD Fp fp_sub(const Fp &a, const Fp &b) {
-    Fp r;
+    Fp d;
+    d.l[0] = sub_cc(a.l[0], b.l[0]);
 #pragma unroll
-    for (int i = 0; i < ZKP_NL; i++) r.l[i] = a.l[i] - b.l[i];
-    ZKP_SETB(r, a.lb + b.lb, a.tb + b.tb, a.vb + b.vb);
+    for (int i = 1; i < ZKP_NL; i++) d.l[i] = subc_cc(a.l[i], b.l[i]);
+    uint32_t mask = subc(0, 0);   // all ones when a < b
+    Fp r;
+    r.l[0] = add_cc(d.l[0], ZKP_2P[0] & mask);
+#pragma unroll
+    for (int i = 1; i < ZKP_NL - 1; i++) r.l[i] = addc_cc(d.l[i], ZKP_2P[i] & mask);
+    r.l[ZKP_NL - 1] = addc(d.l[ZKP_NL - 1], ZKP_2P[ZKP_NL - 1] & mask);
     return r;
 }
-// -a                                         -- src/fp.rs:381-405
+// -a = 2p - a, in [0, 2p]                    -- src/fp.rs:381-405
 ZKP_HD Fp fp_neg(const Fp &a) {
     Fp r;
+    r.l[0] = sub_cc(ZKP_2P[0], a.l[0]);
 #pragma unroll
-    for (int i = 0; i < ZKP_NL; i++) r.l[i] = -a.l[i];
-    ZKP_SETB(r, a.lb, a.tb, a.vb);
+    for (int i = 1; i < ZKP_NL - 1; i++) r.l[i] = subc_cc(ZKP_2P[i], a.l[i]);
+    r.l[ZKP_NL - 1] = subc(ZKP_2P[ZKP_NL - 1], a.l[ZKP_NL - 1]);
     return r;
 }
 ZKP_HD Fp fp_dbl(const Fp &a) { return fp_add(a, a); }
@@ -160,7 +199,7 @@ ZKP_HD Fp fp_xchg(const Fp &a) {
     for (int i = 0; i < ZKP_NL; i++) r.l[i] = word_xchg(a.l[i]);
     return r;
 #else
-    Fp r = a;                      // bounds travel with the value in the tracker build
+    Fp r = a;
     zkp_sim_xchg(&r, sizeof(Fp));
     return r;
 #endif
@@ -170,164 +209,124 @@ ZKP_HD Fp fp_select(bool c, const Fp &a, const Fp &b) {
     Fp r;
 #pragma unroll
     for (int i = 0; i < ZKP_NL; i++) r.l[i] = c ? a.l[i] : b.l[i];
-#ifdef ZKP_TRACK_BOUNDS
-    ZKP_SETB(r, a.lb > b.lb ? a.lb : b.lb, a.tb > b.tb ? a.tb : b.tb, a.vb > b.vb ? a.vb : b.vb);
-#endif
-    return r;
-}
-
-// Weak normalization: one parallel carry round.  l[0..12] end in [-16, 2^28 + 16]; value unchanged.
-ZKP_HD Fp fp_wnorm(const Fp &a) {
-    Fp r;
-    r.l[0] = a.l[0] & ZKP_M28;
-#pragma unroll
-    for (int i = 1; i < ZKP_NL - 1; i++) r.l[i] = (a.l[i] & ZKP_M28) + (a.l[i - 1] >> 28);
-    r.l[ZKP_NL - 1] = a.l[ZKP_NL - 1] + (a.l[ZKP_NL - 2] >> 28);
-    ZKP_SETB(r, 268435456.0 + a.lb / 268435456.0 + 1.0, a.tb + a.lb / 268435456.0 + 1.0, a.vb);
-    return r;
-}
-// Full normalization: serial carry propagation.  l[0..12] end in [0, 2^28); l[13] takes the rest.
-ZKP_HD Fp fp_norm(const Fp &a) {
-    Fp r;
-    int32_t c = 0;
-#pragma unroll
-    for (int i = 0; i < ZKP_NL - 1; i++) {
-        int32_t t = a.l[i] + c;
-        r.l[i] = t & ZKP_M28;
-        c = t >> 28;
-    }
-    r.l[ZKP_NL - 1] = a.l[ZKP_NL - 1] + c;
-    ZKP_SETB(r, 268435455.0, a.tb + a.lb / 268435456.0 + 1.0, a.vb);
-    return r;
-}
-
-// Value reduction for the rare data paths that carry a value through additions only (the z terms
-// of the cyclotomic squaring): subtracts q*p with q = round(v/p) estimated from the top limb, so the
-// result lies in (-0.51p, 0.51p).  Any limb bound below 2^31 and |v| < 1000p are accepted: the
-// multiply-subtract runs in 64 bits (14 IMAD.WIDE) and one carry round brings the limbs back to
-// [-1026, 2^28 + 1026].
-#define ZKP_VREDUCE_K 10322781ll   /* round(2^404 / p) = 2^40 / (p / 2^364) */
-ZKP_HD Fp fp_vreduce(const Fp &a) {
-#ifdef ZKP_TRACK_BOUNDS
-    if (a.vb > 1000.0) zkp_bound_fail("fp_vreduce input value bound", a.vb);
-#endif
-    // the top limb only sees v / 2^364 after the lower limbs' carries are folded in
-    int32_t top = a.l[ZKP_NL - 1] + (a.l[ZKP_NL - 2] >> 28);
-    int32_t q = (int32_t)(((int64_t)top * ZKP_VREDUCE_K + (1ll << 39)) >> 40);
-    Fp r;
-    int64_t x = (int64_t)a.l[0] - (int64_t)q * ZKP_P[0];
-    r.l[0] = (int32_t)((uint32_t)x & ZKP_M28);
-#pragma unroll
-    for (int i = 1; i < ZKP_NL - 1; i++) {
-        int32_t c = (int32_t)(x >> 28);
-        x = (int64_t)a.l[i] - (int64_t)q * ZKP_P[i];
-        r.l[i] = (int32_t)((uint32_t)x & ZKP_M28) + c;
-    }
-    r.l[ZKP_NL - 1] = a.l[ZKP_NL - 1] - q * ZKP_P[ZKP_NL - 1] + (int32_t)(x >> 28);
-    ZKP_SETB(r, 268435456.0 + 1026.0, 0.51 * ZKP_TOP_PER_P + 1030.0, 0.52);
     return r;
 }
 
 // ------------------------------------------------------------------ Montgomery product
 //
-// a*b/2^392 mod p as a normalized value in (ab/R, ab/R + p).  Separated operand scanning over 27
-// 64-bit column accumulators: 196 IMAD.WIDE for a*b, then per reduction step one IMAD (m) and 14
-// IMAD.WIDE.U32 (m*p); no carries anywhere, the columns are resolved by two shifts each.
-// m = (t * n0') mod 2^28 as a plain 32-bit value.  The opaque move keeps the compiler from
-// re-deriving the multiplier as a masked 64-bit quantity (it then emits 64-bit multiplies whose
-// zero high halves survive as an extra add after every IMAD.WIDE).
-ZKP_HD int32_t mont_m(uint32_t t_lo) {
-    int32_t m = (int32_t)((t_lo * ZKP_N0INV) & ZKP_M28);
-#ifdef ZKP_DEVICE_BUILD
-    asm("" : "+r"(m));
-#endif
-    return m;
+// CIOS over two interleaved accumulators.  X is the array in the "even" role (words 0..11 of the
+// running sum), Y the one in the "odd" role (words 1..12).  After every row the sum is divisible
+// by 2^32; instead of shifting registers the arrays swap roles (the old odd array is the new even
+// one, the old even array moves down 64 bits inside the first chain of the next row).
+
+// x[j..j+1] += k[j+OFF]*m for j = 0,2,..,10 (one carry chain, 6 wide MACs); leaves carry-out in CF
+template <int OFF>
+ZKP_HD void chain_mad(uint32_t *x, const uint32_t *k, uint32_t m) {
+    x[0] = mad_lo_cc(k[OFF], m, x[0]);
+    x[1] = madc_hi_cc(k[OFF], m, x[1]);
+#pragma unroll
+    for (int j = 2; j < ZKP_NL; j += 2) {
+        x[j] = madc_lo_cc(k[j + OFF], m, x[j]);
+        x[j + 1] = madc_hi_cc(k[j + OFF], m, x[j + 1]);
+    }
 }
-// reduction half shared by the one- and two-product forms: col[0..26] -> normalized limbs
-ZKP_HD Fp mont_reduce(int64_t *col) {
-    int64_t carry = 0;
+// y >>= 64 bits; y[j..j+1] += a[j+1]*m for j = 0,2,..,10, consuming the incoming carry
+ZKP_HD void chain_mad_rshift(uint32_t *y, const uint32_t *a, uint32_t m) {
 #pragma unroll
-    for (int k = 0; k < ZKP_NL; k++) {
-        int64_t t = col[k] + carry;
-        int32_t m = mont_m((uint32_t)t);
-        t += (int64_t)m * (int64_t)ZKP_P[0];
-        carry = t >> 28;   // exact: the low 28 bits of t are zero now
-#pragma unroll
-        for (int j = 1; j < ZKP_NL; j++) col[k + j] += (int64_t)m * (int64_t)ZKP_P[j];
+    for (int j = 0; j < ZKP_NL - 2; j += 2) {
+        y[j] = madc_lo_cc(a[j + 1], m, y[j + 2]);
+        y[j + 1] = madc_hi_cc(a[j + 1], m, y[j + 3]);
     }
+    y[ZKP_NL - 2] = madc_lo_cc(a[ZKP_NL - 1], m, 0);
+    y[ZKP_NL - 1] = madc_hi(a[ZKP_NL - 1], m, 0);
+}
+// x/y += k*m over both chains; the carry out of the even chain lands in the top odd word.  The
+// carry out of the odd chain is zero by the operand bounds (top words: u,w <= 0x68044800,
+// p = 0x1a0111ea; their sum stays below 2^32).
+ZKP_HD void row_mad(uint32_t *x, uint32_t *y, const uint32_t *k, uint32_t m) {
+    chain_mad<1>(y, k, m);
+    chain_mad<0>(x, k, m);
+    y[ZKP_NL - 1] = addc(y[ZKP_NL - 1], 0);
+}
+// reduction half of a row: m = x0 * n0'; x/y += p*m
+ZKP_HD void row_reduce(uint32_t *x, uint32_t *y) {
+    uint32_t m = x[0] * ZKP_N0INV;
+    row_mad(x, y, ZKP_P, m);
+}
+// first row: disjoint 64-bit products, no carries
+ZKP_HD void row_first(uint32_t *x, uint32_t *y, const uint32_t *a, uint32_t b0) {
+#pragma unroll
+    for (int j = 0; j < ZKP_NL; j += 2) {
+        uint64_t e = (uint64_t)a[j] * b0;
+        uint64_t o = (uint64_t)a[j + 1] * b0;
+        x[j] = (uint32_t)e;
+        x[j + 1] = (uint32_t)(e >> 32);
+        y[j] = (uint32_t)o;
+        y[j + 1] = (uint32_t)(o >> 32);
+    }
+}
+// later rows: x = array entering the even role, y = array entering the odd role
+ZKP_HD void row_next(uint32_t *x, uint32_t *y, const uint32_t *a, uint32_t bi) {
+    x[0] = add_cc(x[0], y[1]);
+    chain_mad_rshift(y, a, bi);
+    chain_mad<0>(x, a, bi);
+    y[ZKP_NL - 1] = addc(y[ZKP_NL - 1], 0);
+}
+// after row 11 the even role is `od` (od[0] == 0): T = ev + (od >> 32)
+ZKP_HD Fp mont_finish(const uint32_t *ev, const uint32_t *od) {
     Fp r;
+    r.l[0] = add_cc(ev[0], od[1]);
 #pragma unroll
-    for (int k = ZKP_NL; k < 2 * ZKP_NL - 1; k++) {
-        int64_t t = col[k] + carry;
-        r.l[k - ZKP_NL] = (int32_t)((uint32_t)t & ZKP_M28);
-        carry = t >> 28;
-    }
-    r.l[ZKP_NL - 1] = (int32_t)carry;
+    for (int k = 1; k < ZKP_NL - 1; k++) r.l[k] = addc_cc(ev[k], od[k + 1]);
+    r.l[ZKP_NL - 1] = addc(ev[ZKP_NL - 1], 0);
     return r;
+}
+
+// a*b/2^384 mod p in [0, 2p).  Needs a*b < p * 2^384: both <= 2p, or one <= 4p and the other <= 2p.
+// 300 wide MACs.  `b` may live in constant memory (its words are only used as scalars).
+ZKP_HD Fp mont_mul(const Fp &a, const uint32_t *b) {
+    uint32_t ev[ZKP_NL], od[ZKP_NL];
+    row_first(ev, od, a.l, b[0]);
+    row_reduce(ev, od);
+#pragma unroll
+    for (int i = 1; i < ZKP_NL; i += 2) {
+        row_next(od, ev, a.l, b[i]);
+        row_reduce(od, ev);
+        if (i + 1 < ZKP_NL) {
+            row_next(ev, od, a.l, b[i + 1]);
+            row_reduce(ev, od);
+        }
+    }
+    return mont_finish(ev, od);
 }
 ZKP_HD Fp mont_mul(const Fp &a, const Fp &b) {
-#ifdef ZKP_TRACK_BOUNDS
-    {
-        double A = a.lb > a.tb ? a.lb : a.tb, B = b.lb > b.tb ? b.lb : b.tb;
-        double col = 14.0 * A * B + 14.0 * 72057594037927936.0 + 1099511627776.0;
-        if (col > g_max_col) g_max_col = col;
-        if (col >= 9.2e18) zkp_bound_fail("column accumulator reaches 2^63 in mont_mul", col);
-        if (a.vb * b.vb / ZKP_R_OVER_P + 1.0 > 2000.0) zkp_bound_fail("product value bound", a.vb * b.vb);
-    }
+#ifndef ZKP_DEVICE_BUILD
+    ZKP_SIM_ASSERT((fp_leq_2p(a) && fp_leq_4p(b)) || (fp_leq_4p(a) && fp_leq_2p(b)), "mont_mul operand bound");
 #endif
-    int64_t col[2 * ZKP_NL - 1];
-#pragma unroll
-    for (int j = 0; j < ZKP_NL; j++) col[j] = (int64_t)a.l[0] * (int64_t)b.l[j];
-#pragma unroll
-    for (int i = 1; i < ZKP_NL; i++) {
-#pragma unroll
-        for (int j = 0; j < ZKP_NL - 1; j++) col[i + j] += (int64_t)a.l[i] * (int64_t)b.l[j];
-        col[i + ZKP_NL - 1] = (int64_t)a.l[i] * (int64_t)b.l[ZKP_NL - 1];
-    }
-    Fp r = mont_reduce(col);
-#ifdef ZKP_TRACK_BOUNDS
-    {
-        double vb = a.vb * b.vb / ZKP_R_OVER_P + 1.0;
-        ZKP_SETB(r, 268435455.0, vb * ZKP_TOP_PER_P + 2.0, vb);
-    }
-#endif
-    return r;
+    return mont_mul(a, b.l);
 }
-// (u*v + w*z)/2^392 mod p with ONE reduction (lazy "sum of products"): 392 + 210 IMADs.  This is
-// one lane's half of an Fp2 product.  Needs 14*(|u||v| + |w||z|) + 2^60 < 2^63.
+// (u*v + w*z)/2^384 mod p in [0, 2p) with ONE reduction (lazy "sum of products"): 288 + 156 wide
+// MACs.  This is one lane's half of an Fp2 product.  All four operands <= 2p.
 ZKP_HD Fp mont_mul2(const Fp &u, const Fp &v, const Fp &w, const Fp &z) {
-#ifdef ZKP_TRACK_BOUNDS
-    {
-        double U = u.lb > u.tb ? u.lb : u.tb, V = v.lb > v.tb ? v.lb : v.tb;
-        double W = w.lb > w.tb ? w.lb : w.tb, Z = z.lb > z.tb ? z.lb : z.tb;
-        double col = 14.0 * (U * V + W * Z) + 14.0 * 72057594037927936.0 + 1099511627776.0;
-        if (col > g_max_col) g_max_col = col;
-        if (col >= 9.2e18) zkp_bound_fail("column accumulator reaches 2^63 in mont_mul2", col);
-        if ((u.vb * v.vb + w.vb * z.vb) / ZKP_R_OVER_P + 1.0 > 2000.0) zkp_bound_fail("product value bound", u.vb * v.vb + w.vb * z.vb);
-    }
+#ifndef ZKP_DEVICE_BUILD
+    ZKP_SIM_ASSERT(fp_leq_2p(u) && fp_leq_2p(v) && fp_leq_2p(w) && fp_leq_2p(z), "mont_mul2 operand bound");
 #endif
-    int64_t col[2 * ZKP_NL - 1];
+    uint32_t ev[ZKP_NL], od[ZKP_NL];
+    row_first(ev, od, u.l, v.l[0]);
+    row_mad(ev, od, w.l, z.l[0]);
+    row_reduce(ev, od);
 #pragma unroll
-    for (int j = 0; j < ZKP_NL; j++) col[j] = (int64_t)u.l[0] * (int64_t)v.l[j];
-#pragma unroll
-    for (int i = 1; i < ZKP_NL; i++) {
-#pragma unroll
-        for (int j = 0; j < ZKP_NL - 1; j++) col[i + j] += (int64_t)u.l[i] * (int64_t)v.l[j];
-        col[i + ZKP_NL - 1] = (int64_t)u.l[i] * (int64_t)v.l[ZKP_NL - 1];
+    for (int i = 1; i < ZKP_NL; i += 2) {
+        row_next(od, ev, u.l, v.l[i]);
+        row_mad(od, ev, w.l, z.l[i]);
+        row_reduce(od, ev);
+        if (i + 1 < ZKP_NL) {
+            row_next(ev, od, u.l, v.l[i + 1]);
+            row_mad(ev, od, w.l, z.l[i + 1]);
+            row_reduce(ev, od);
+        }
     }
-#pragma unroll
-    for (int i = 0; i < ZKP_NL; i++) {
-#pragma unroll
-        for (int j = 0; j < ZKP_NL; j++) col[i + j] += (int64_t)w.l[i] * (int64_t)z.l[j];
-    }
-    Fp r = mont_reduce(col);
-#ifdef ZKP_TRACK_BOUNDS
-    {
-        double vb = (u.vb * v.vb + w.vb * z.vb) / ZKP_R_OVER_P + 1.0;
-        ZKP_SETB(r, 268435455.0, vb * ZKP_TOP_PER_P + 2.0, vb);
-    }
-#endif
-    return r;
+    return mont_finish(ev, od);
 }
 // Value-equivalent (after conversion) to src/fp.rs:413-434 / :452-455.
 ZKP_HD Fp fp_mul(const Fp &a, const Fp &b) { return mont_mul(a, b); }
@@ -336,77 +335,37 @@ ZKP_HD Fp fp_mul(const Fp &a, const Fp &b) { return mont_mul(a, b); }
 //
 // Canonical form = 12 saturated 32-bit words (= the six u64 limbs of src/fp.rs:24), value in [0,p).
 
-// true when w < p
-ZKP_HD bool words_lt_p(const uint32_t *w) {
-    int64_t borrow = 0;
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-        int64_t d = (int64_t)w[i] - (int64_t)ZKP_P32[i] + borrow;
-        borrow = d >> 32;   // 0 or -1
-    }
-    return borrow != 0;
-}
 // canonical words -> Montgomery Fp; sets bad when w >= p (such inputs are rejected at the boundary
 // because the reference's neg is undefined there, src/fp.rs:383-405)
 ZKP_HD Fp fp_from_words(const uint32_t *w, bool &bad) {
-    bad = bad | !words_lt_p(w);
     Fp a;
 #pragma unroll
-    for (int i = 0; i < ZKP_NL; i++) {
-        const int bit = 28 * i, idx = bit >> 5, sh = bit & 31;
-        uint32_t lo = w[idx] >> sh;
-        uint32_t hi = (sh > 4 && idx + 1 < 12) ? (w[idx + 1] << (32 - sh)) : 0u;
-        a.l[i] = (int32_t)((lo | hi) & ZKP_M28);
-    }
-    ZKP_SETB(a, 268435455.0, 16777216.0, 10.0);   // any 384-bit input (even a rejected one) stays in range
-    return mont_mul(a, fp_const(ZKP_R2));
+    for (int i = 0; i < ZKP_NL; i++) a.l[i] = w[i];
+    bad = bad | fp_geq_const(a, ZKP_P);
+    return mont_mul(a, ZKP_R2);   // any 384-bit a: a * R2 < 2^384 * p, result in [0, 2p)
 }
-// Montgomery Fp (any lazily reduced value the tracker allows) -> canonical words in [0,p)
+// Montgomery Fp (2p-redundant) -> canonical words in [0,p)
 ZKP_HD void fp_to_words(uint32_t *w, const Fp &m) {
-    Fp one = fp_zero();
-    one.l[0] = 1;
-    ZKP_SETB(one, 1.0, 0.0, 1.0);
-    Fp t = mont_mul(m, one);                 // value in (-0.8p, 1.8p) for |m| < 2000p
-    t = fp_norm(fp_add(t, fp_const(ZKP_P))); // + p: strictly positive, fully normalized
-    uint64_t acc = 0;
-    int have = 0, wi = 0;
-    uint32_t v[13];
+    uint32_t one[ZKP_NL];
+    one[0] = 1;
 #pragma unroll
-    for (int i = 0; i < ZKP_NL; i++) {
-        acc |= (uint64_t)(uint32_t)t.l[i] << have;
-        have += 28;
-        if (have >= 32) {
-            v[wi++] = (uint32_t)acc;
-            acc >>= 32;
-            have -= 32;
-        }
-    }
-    v[wi] = (uint32_t)acc;   // wi == 12 here; bits 384.. (zero: value < 3p < 2^384)
-    // value < 2.8p: two conditional subtractions of p
+    for (int i = 1; i < ZKP_NL; i++) one[i] = 0;
+    Fp t = mont_mul(m, one);   // (m + k*p)/R <= p
+    Fp d;
+    d.l[0] = sub_cc(t.l[0], ZKP_P[0]);
 #pragma unroll
-    for (int rep = 0; rep < 2; rep++) {
-        uint32_t d[12];
-        int64_t borrow = 0;
+    for (int i = 1; i < ZKP_NL; i++) d.l[i] = subc_cc(t.l[i], ZKP_P[i]);
+    bool lt = subc(0, 0) != 0;
 #pragma unroll
-        for (int i = 0; i < 12; i++) {
-            int64_t x = (int64_t)v[i] - (int64_t)ZKP_P32[i] + borrow;
-            d[i] = (uint32_t)x;
-            borrow = x >> 32;
-        }
-        bool ge = borrow == 0;
-#pragma unroll
-        for (int i = 0; i < 12; i++) v[i] = ge ? d[i] : v[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 12; i++) w[i] = v[i];
+    for (int i = 0; i < ZKP_NL; i++) w[i] = lt ? t.l[i] : d.l[i];
 }
 // Comparisons go through the canonical form (rare: flags and degenerate cases of the group law).
 ZKP_HD bool fp_is_zero(const Fp &a) {
-    uint32_t w[12];
+    uint32_t w[ZKP_NL];
     fp_to_words(w, a);
     uint32_t t = 0;
 #pragma unroll
-    for (int i = 0; i < 12; i++) t |= w[i];
+    for (int i = 0; i < ZKP_NL; i++) t |= w[i];
     return t == 0;
 }
 

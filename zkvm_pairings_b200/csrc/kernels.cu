@@ -3,7 +3,8 @@
 // A LANE PAIR (two adjacent threads) owns one pairing check (k pairs -> shared-accumulator Miller
 // loop -> final exponentiation): every Fp2 of the tower is split over the pair (tower.cuh), so a
 // warp runs 16 independent checks in lock-step (the control flow is data independent) and the
-// integer-multiply pipe is kept busy by the carry-free 28-bit-limb Montgomery products of fp.cuh.  Independent checks shard in contiguous slices over the context's devices;
+// integer-multiply pipe is kept busy by the carry-chained 32-bit-limb Montgomery products of
+// fp.cuh.  Independent checks shard in contiguous slices over the context's devices;
 // the only cross-device traffic is the 576-byte Fp12 partial of zkp_multi_miller_product.
 //
 // There is deliberately no CPU implementation in this library: with no CUDA device every entry
@@ -20,7 +21,6 @@
 
 #include "../../include/zkpair.h"
 #include "ops.cuh"
-#include "cios32_probe.cuh"
 
 #ifndef ZKP_TPB
 #define ZKP_TPB 128           // threads per block of the pairing kernels
@@ -95,31 +95,37 @@ k_gen_points(uint64_t seed, uint64_t first, size_t n, uint64_t *__restrict__ g1,
     gen_g2_one(b, g2 + 24 * i, g2inf + i);
 }
 
-// Integer-multiply roofline probe.  KIND 0: 8 independent IMAD.WIDE.U32 accumulate chains per
-// thread; KIND 1: 8 independent 32-bit IMAD chains; KIND 2: the carry-chained wide MACs exactly as
-// the Montgomery rows issue them (two 6-MAC chains per step).
+// Integer-multiply roofline probe.  Every chain gets its own multiplier and the multiplicand changes
+// every iteration, so nothing is loop invariant (ptxas would otherwise hoist the product and leave
+// 64-bit adds).  KIND 0: 8 independent IMAD.WIDE.U32 accumulate chains per thread; KIND 1: 8
+// independent 32-bit IMAD chains; KIND 2: the carry-chained wide MACs exactly as the Montgomery
+// rows of fp.cuh issue them (row_mad: two 6-MAC carry chains per step).
 template <int KIND>
 __global__ void __launch_bounds__(256) k_imad_peak(uint32_t *sink, int iters) {
     uint32_t x = threadIdx.x * 2654435761u + 12345u, y = blockIdx.x * 40503u + 977u;
+    uint32_t m = x;
     if (KIND == 0) {
         uint64_t acc[8];
+        uint32_t ys[8];
 #pragma unroll
-        for (int c = 0; c < 8; c++) acc[c] = x + c;
+        for (int c = 0; c < 8; c++) { acc[c] = x + c; ys[c] = y * (2 * c + 3) + sink[1]; }
         for (int it = 0; it < iters; it++) {
+            m = m * 1664525u + 1013904223u;
 #pragma unroll
-            for (int c = 0; c < 8; c++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(x), "r"(y));
+            for (int c = 0; c < 8; c++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(m), "r"(ys[c]));
         }
         uint64_t s = 0;
 #pragma unroll
         for (int c = 0; c < 8; c++) s ^= acc[c];
         if (s == 0x123456789abcdefull) sink[0] = (uint32_t)s;
     } else if (KIND == 1) {
-        uint32_t acc[8];
+        uint32_t acc[8], ys[8];
 #pragma unroll
-        for (int c = 0; c < 8; c++) acc[c] = x + c;
+        for (int c = 0; c < 8; c++) { acc[c] = x + c; ys[c] = y * (2 * c + 3) + sink[1]; }
         for (int it = 0; it < iters; it++) {
+            m = m * 1664525u + 1013904223u;
 #pragma unroll
-            for (int c = 0; c < 8; c++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[c]) : "r"(x), "r"(y));
+            for (int c = 0; c < 8; c++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[c]) : "r"(m), "r"(ys[c]));
         }
         uint32_t s = 0;
 #pragma unroll
@@ -128,10 +134,10 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t *sink, int iters) {
     } else {
         uint32_t ev[12], od[12], a[12];
 #pragma unroll
-        for (int c = 0; c < 12; c++) { ev[c] = x + c; od[c] = y + c; a[c] = x * (c + 3) + y; }
+        for (int c = 0; c < 12; c++) { ev[c] = x + c; od[c] = y + c; a[c] = x * (c + 3) + y + sink[1]; }
         for (int it = 0; it < iters; it++) {
-            chain_mad<0>(ev, a, y);
-            chain_mad<1>(od, a, x);
+            m = m * 1664525u + 1013904223u;
+            row_mad(ev, od, a, m);
         }
         uint32_t s = 0;
 #pragma unroll
@@ -258,7 +264,7 @@ const char *zkp_last_error(void) { return g_err.c_str(); }
 
 const char *zkp_version(void) {
     static char buf[160];
-    snprintf(buf, sizeof buf, "zkpair 0.1 (sm_100a, tpb=%d, min_blocks=%d, chunk=%u)", ZKP_TPB, ZKP_MIN_BLOCKS, (unsigned)ZKP_CHUNK);
+    snprintf(buf, sizeof buf, "zkpair 0.2 (sm_100a, 2 lanes/pairing, 12x32 CIOS, tpb=%d, min_blocks=%d, chunk=%u)", ZKP_TPB, ZKP_MIN_BLOCKS, (unsigned)ZKP_CHUNK);
     return buf;
 }
 
@@ -293,8 +299,8 @@ int32_t zkp_ctx_create(const int *devices, int n_devices, zkp_ctx **out) {
         cudaError_t e = cudaSetDevice(d.id);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream[0], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream[1], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaMalloc(&d.d_err, sizeof(uint32_t));
-        if (e == cudaSuccess) e = cudaMemset(d.d_err, 0, sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&d.d_err, 4 * sizeof(uint32_t));   // [0] error flag, [1] zero word read by the probes
+        if (e == cudaSuccess) e = cudaMemset(d.d_err, 0, 4 * sizeof(uint32_t));
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, d.id);
         if (e != cudaSuccess) {
             std::string msg = std::string("device init failed: ") + cudaGetErrorString(e);

@@ -19,22 +19,22 @@ ZKP_NOINLINE void doubling_step(G2P &r, Fp2 *co) {
     Fp2 t0 = fp2_sqr(r.x);
     Fp2 t1 = fp2_sqr(r.y);
     Fp2 t2 = fp2_sqr(t1);
-    Fp2 t3 = fp2_sub(fp2_sub(fp2_sqr(fp2_wnorm(fp2_add(t1, r.x))), t0), t2);
-    t3 = fp2_wnorm(fp2_dbl(t3));
-    Fp2 t4 = fp2_wnorm(fp2_add(fp2_dbl(t0), t0));
-    Fp2 t6 = fp2_wnorm(fp2_add(r.x, t4));
+    Fp2 t3 = fp2_sub(fp2_sub(fp2_sqr(fp2_add(t1, r.x)), t0), t2);
+    t3 = fp2_dbl(t3);
+    Fp2 t4 = fp2_add(fp2_dbl(t0), t0);
+    Fp2 t6 = fp2_add(r.x, t4);
     Fp2 t5 = fp2_sqr(t4);
     Fp2 zz = fp2_sqr(r.z);
-    Fp2 xn = fp2_vreduce(fp2_sub(fp2_sub(t5, t3), t3));
-    Fp2 zn = fp2_vreduce(fp2_sub(fp2_sub(fp2_sqr(fp2_wnorm(fp2_add(r.z, r.y))), t1), zz));
-    Fp2 yn = fp2_mul(fp2_wnorm(fp2_sub(t3, xn)), t4);
-    t2 = fp2_wnorm(fp2_dbl(fp2_dbl(t2)));
-    r.y = fp2_vreduce(fp2_sub(yn, fp2_dbl(t2)));
+    Fp2 xn = fp2_sub(fp2_sub(t5, t3), t3);
+    Fp2 zn = fp2_sub(fp2_sub(fp2_sqr(fp2_add(r.z, r.y)), t1), zz);
+    Fp2 yn = fp2_mul(fp2_sub(t3, xn), t4);
+    t2 = fp2_dbl(fp2_dbl(t2));
+    r.y = fp2_sub(yn, fp2_dbl(t2));
     r.x = xn;
     r.z = zn;
     co[1] = fp2_neg(fp2_dbl(fp2_mul(t4, zz)));
     t6 = fp2_sub(fp2_sub(fp2_sqr(t6), t0), t5);
-    co[2] = fp2_wnorm(fp2_sub(t6, fp2_dbl(fp2_dbl(t1))));
+    co[2] = fp2_sub(t6, fp2_dbl(fp2_dbl(t1)));
     co[0] = fp2_dbl(fp2_mul(zn, zz));
 }
 
@@ -43,24 +43,24 @@ ZKP_NOINLINE void addition_step(G2P &r, const G2A &q, Fp2 *co) {
     Fp2 zz = fp2_sqr(r.z);
     Fp2 yy = fp2_sqr(q.y);
     Fp2 t0 = fp2_mul(zz, q.x);
-    Fp2 t1 = fp2_mul(fp2_wnorm(fp2_sub(fp2_sub(fp2_sqr(fp2_wnorm(fp2_add(q.y, r.z))), yy), zz)), zz);
-    Fp2 t2 = fp2_wnorm(fp2_sub(t0, r.x));
+    Fp2 t1 = fp2_mul(fp2_sub(fp2_sub(fp2_sqr(fp2_add(q.y, r.z)), yy), zz), zz);
+    Fp2 t2 = fp2_sub(t0, r.x);
     Fp2 t3 = fp2_sqr(t2);
-    Fp2 t4 = fp2_wnorm(fp2_dbl(fp2_dbl(t3)));
+    Fp2 t4 = fp2_dbl(fp2_dbl(t3));
     Fp2 t5 = fp2_mul(t4, t2);
-    Fp2 t6 = fp2_wnorm(fp2_sub(fp2_sub(t1, r.y), r.y));
+    Fp2 t6 = fp2_sub(fp2_sub(t1, r.y), r.y);
     Fp2 t9 = fp2_mul(t6, q.x);
     Fp2 t7 = fp2_mul(t4, r.x);
-    Fp2 xn = fp2_vreduce(fp2_sub(fp2_sub(fp2_sub(fp2_sqr(t6), t5), t7), t7));
-    Fp2 zn = fp2_vreduce(fp2_sub(fp2_sub(fp2_sqr(fp2_wnorm(fp2_add(r.z, t2))), zz), t3));
-    Fp2 t10 = fp2_wnorm(fp2_add(q.y, zn));
-    Fp2 t8 = fp2_mul(fp2_wnorm(fp2_sub(t7, xn)), t6);
+    Fp2 xn = fp2_sub(fp2_sub(fp2_sub(fp2_sqr(t6), t5), t7), t7);
+    Fp2 zn = fp2_sub(fp2_sub(fp2_sqr(fp2_add(r.z, t2)), zz), t3);
+    Fp2 t10 = fp2_add(q.y, zn);
+    Fp2 t8 = fp2_mul(fp2_sub(t7, xn), t6);
     t0 = fp2_dbl(fp2_mul(r.y, t5));
-    r.y = fp2_vreduce(fp2_sub(t8, t0));
+    r.y = fp2_sub(t8, t0);
     r.x = xn;
     r.z = zn;
     t10 = fp2_sub(fp2_sub(fp2_sqr(t10), yy), fp2_sqr(zn));
-    co[2] = fp2_wnorm(fp2_sub(fp2_dbl(t9), t10));
+    co[2] = fp2_sub(fp2_dbl(t9), t10);
     co[0] = fp2_dbl(zn);
     co[1] = fp2_dbl(fp2_neg(t6));
 }
@@ -164,8 +164,8 @@ ZKP_HD void final_exponentiation(Fp12 &r, const Fp12 &f) {
 // Field-generic via small traits.
 struct OpsFp {
     typedef Fp T;
-    static ZKP_MEMBER T add(const T &a, const T &b) { return fp_wnorm(fp_add(a, b)); }
-    static ZKP_MEMBER T sub(const T &a, const T &b) { return fp_wnorm(fp_sub(a, b)); }
+    static ZKP_MEMBER T add(const T &a, const T &b) { return fp_add(a, b); }
+    static ZKP_MEMBER T sub(const T &a, const T &b) { return fp_sub(a, b); }
     static ZKP_MEMBER T mul(const T &a, const T &b) { return fmul(a, b); }
     static ZKP_MEMBER T sqr(const T &a) { return fsqr(a); }
     static ZKP_MEMBER T inv(const T &a) { return fp_inv(a); }
@@ -175,8 +175,8 @@ struct OpsFp {
 };
 struct OpsFp2 {
     typedef Fp2 T;
-    static ZKP_MEMBER T add(const T &a, const T &b) { return fp2_wnorm(fp2_add(a, b)); }
-    static ZKP_MEMBER T sub(const T &a, const T &b) { return fp2_wnorm(fp2_sub(a, b)); }
+    static ZKP_MEMBER T add(const T &a, const T &b) { return fp2_add(a, b); }
+    static ZKP_MEMBER T sub(const T &a, const T &b) { return fp2_sub(a, b); }
     static ZKP_MEMBER T mul(const T &a, const T &b) { return fp2_mul(a, b); }
     static ZKP_MEMBER T sqr(const T &a) { return fp2_sqr(a); }
     static ZKP_MEMBER T inv(const T &a) { return fp2_inv(a); }

@@ -7,21 +7,17 @@
 // (src/fp2.rs:192-209) and 36-mul interleaved Fp6 (src/fp6.rs:188-267).
 //
 // Work split: TWO lanes per pairing.  Every Fp2 is split over an even/odd lane pair (see the Fp2
-// section), so a thread carries half of the tower state (an Fp12 is 6 x 14 registers per lane)
+// section), so a thread carries half of the tower state (an Fp12 is 6 x 12 registers per lane)
 // and the Fp6-level working sets fit the register file.
 //
-// Code-size / register strategy: the Fp2 product and square (602 / 420 IMADs per lane) are
-// out-of-line functions whose operands and result travel in registers (28 in, 14 out), so their
-// bodies stay hot in the instruction cache.  Additions are inlined (14 carry-free adds per lane);
-// Fp6-level and larger operations are out-of-line and exchange operands through thread-local
-// memory.
+// Code-size / register strategy: the Fp2 product and square (444 / 300 wide MACs per lane) are
+// out-of-line functions whose operands and result travel in registers (24 in, 12 out), so their
+// bodies stay hot in the instruction cache.  Additions are inlined; Fp6-level and larger
+// operations are out-of-line and exchange operands through thread-local memory.
 //
-// Lazy reduction: additions never reduce; products come back normalized.  Every Fp2
-// product/square weakly normalizes its outputs (fp_wnorm, one parallel carry round) so limb
-// magnitudes stay far below 2^31, and every Fp6-level function value-reduces its outputs
-// (fp_vreduce, |v| < 0.52p) so the value bounds cannot compound through chains of products.  The
-// bound tracker of the CPU dev simulation (ZKP_TRACK_BOUNDS) proves the worst case over the whole
-// pairing: the bounds depend on the formula DAG only, never on the data.
+// Reduction discipline: every Fp is kept 2p-redundant (fp.cuh): additions and subtractions correct
+// by +-2p, products come back below 2p, so any two values can be multiplied without further
+// thought.  The one lazy spot is the Fp2 squaring (one operand is an uncorrected sum <= 4p).
 #pragma once
 #include "fp.cuh"
 
@@ -37,9 +33,9 @@ ZKP_NOINLINE Fp fp_inv(Fp a) {
     Fp res = a;   // bit 380 of p-2 is set
     for (int i = 379; i >= 0; i--) {
         res = fsqr(res);
-        int limb = i / 28;
-        uint32_t w = (uint32_t)ZKP_P[limb] - (limb == 0 ? 2u : 0u);   // limbs of p-2 (no borrow: p0 = ...aaab)
-        if ((w >> (i - 28 * limb)) & 1) res = fmul(res, a);
+        int limb = i >> 5;
+        uint32_t w = ZKP_P[limb] - (limb == 0 ? 2u : 0u);   // words of p-2 (no borrow: p0 = ...aaab)
+        if ((w >> (i & 31)) & 1) res = fmul(res, a);
     }
     return res;
 }
@@ -47,11 +43,11 @@ ZKP_NOINLINE Fp fp_inv(Fp a) {
 // ------------------------------------------------------------------ Fp2 (split over a lane pair)
 //
 // An Fp2 value a0 + a1*u lives in TWO adjacent lanes: the even lane holds a0, the odd lane a1.
-// Additions are lane-local; a product costs each lane one exchange (2 x 14 shfl.xor) and one lazy
+// Additions are lane-local; a product costs each lane one exchange (2 x 12 shfl.xor) and one lazy
 // "two products, one reduction" (fp.cuh mont_mul2):
 //     even lane:  c0 = a0*b0 - a1*b1            odd lane:  c1 = a0*b1 + a1*b0
 // i.e. the schoolbook form of src/fp2.rs:192-209, which with a single reduction per lane costs
-// 2*(392+210) = 1204 IMADs per Fp2 product against 3*420 = 1260 for Karatsuba over full Fp
+// 2*(288+156) = 888 wide MACs per Fp2 product against 3*300 = 900 for Karatsuba over full Fp
 // products -- and both lanes do identical work, so there is no divergence and no idle lane.
 struct Fp2 {
     Fp c;   // c0 in even lanes, c1 in odd lanes
@@ -59,11 +55,9 @@ struct Fp2 {
 
 ZKP_HD Fp2 fp2_zero() { Fp2 r; r.c = fp_zero(); return r; }
 ZKP_HD Fp2 fp2_one() { Fp2 r; r.c = fp_select(lane_par() != 0, fp_zero(), fp_one()); return r; }
-// constant stored as c0 | c1 (2 x 14 limbs, Montgomery form)
-ZKP_HD Fp2 fp2_const(const int32_t *k) { Fp2 r; r.c = fp_const(k + lane_par() * ZKP_NL); return r; }
+// constant stored as c0 | c1 (2 x 12 words, Montgomery form)
+ZKP_HD Fp2 fp2_const(const uint32_t *k) { Fp2 r; r.c = fp_const(k + lane_par() * ZKP_NL); return r; }
 ZKP_HD bool fp2_is_zero(const Fp2 &a) { return lane_and(fp_is_zero(a.c)); }
-ZKP_HD Fp2 fp2_vreduce(const Fp2 &a) { Fp2 r; r.c = fp_vreduce(a.c); return r; }
-ZKP_HD Fp2 fp2_wnorm(const Fp2 &a) { Fp2 r; r.c = fp_wnorm(a.c); return r; }
 ZKP_HD Fp2 fp2_add(const Fp2 &a, const Fp2 &b) { Fp2 r; r.c = fp_add(a.c, b.c); return r; }   // src/fp2.rs:216-218
 ZKP_HD Fp2 fp2_sub(const Fp2 &a, const Fp2 &b) { Fp2 r; r.c = fp_sub(a.c, b.c); return r; }   // src/fp2.rs:221-223
 ZKP_HD Fp2 fp2_neg(const Fp2 &a) { Fp2 r; r.c = fp_neg(a.c); return r; }                      // src/fp2.rs:226-228
@@ -77,8 +71,7 @@ ZKP_HD Fp2 fp2_mul_nr(const Fp2 &a) {
     r.c = fp_add(a.c, fp_select(lane_par() != 0, t, fp_neg(t)));
     return r;
 }
-// Product.  Operand limb bounds La, Lb need 28*La*Lb + 2^60 < 2^63: each operand may be a sum of
-// two normalized values.  The result is a normalized product.
+// Product; operands and result 2p-redundant.
 ZKP_NOINLINE Fp2 fp2_mul(Fp2 a, Fp2 b) {
     bool odd = lane_par() != 0;
     Fp pa = fp_xchg(a.c), pb = fp_xchg(b.c);
@@ -89,11 +82,11 @@ ZKP_NOINLINE Fp2 fp2_mul(Fp2 a, Fp2 b) {
     return r;
 }
 // Square (complex method, src/fp2.rs:171-189): even lane (a0+a1)(a0-a1), odd lane (2 a0) a1.
-// The operand must be (weakly) normalized.
+// x is an uncorrected sum (<= 4p), y is 2p-redundant: x*y <= 8p^2 as mont_mul requires.
 ZKP_NOINLINE Fp2 fp2_sqr(Fp2 a) {
     bool odd = lane_par() != 0;
     Fp pa = fp_xchg(a.c);
-    Fp x = fp_add(pa, fp_select(odd, pa, a.c));
+    Fp x = fp_add_lazy(pa, fp_select(odd, pa, a.c));
     Fp y = fp_select(odd, a.c, fp_sub(a.c, pa));
     Fp2 r;
     r.c = mont_mul(x, y);
@@ -115,8 +108,6 @@ struct Fp6 {
     Fp2 c0, c1, c2;
 };
 
-ZKP_HD void fp6_vreduce(Fp6 &r, const Fp6 &a) { r.c0 = fp2_vreduce(a.c0); r.c1 = fp2_vreduce(a.c1); r.c2 = fp2_vreduce(a.c2); }
-ZKP_HD void fp6_wnorm(Fp6 &r, const Fp6 &a) { r.c0 = fp2_wnorm(a.c0); r.c1 = fp2_wnorm(a.c1); r.c2 = fp2_wnorm(a.c2); }
 ZKP_HD void fp6_set_zero(Fp6 &r) { r.c0 = fp2_zero(); r.c1 = fp2_zero(); r.c2 = fp2_zero(); }
 ZKP_HD void fp6_add(Fp6 &r, const Fp6 &a, const Fp6 &b) { r.c0 = fp2_add(a.c0, b.c0); r.c1 = fp2_add(a.c1, b.c1); r.c2 = fp2_add(a.c2, b.c2); }   // src/fp6.rs:322-333
 ZKP_HD void fp6_sub(Fp6 &r, const Fp6 &a, const Fp6 &b) { r.c0 = fp2_sub(a.c0, b.c0); r.c1 = fp2_sub(a.c1, b.c1); r.c2 = fp2_sub(a.c2, b.c2); }   // src/fp6.rs:358-367
@@ -133,31 +124,31 @@ ZKP_NOINLINE void fp6_mul(Fp6 &r, const Fp6 &a, const Fp6 &b) {
     Fp2 v0 = fp2_mul(a.c0, b.c0);
     Fp2 v1 = fp2_mul(a.c1, b.c1);
     Fp2 v2 = fp2_mul(a.c2, b.c2);
-    Fp2 t0 = fp2_sub(fp2_sub(fp2_mul(fp2_wnorm(fp2_add(a.c1, a.c2)), fp2_wnorm(fp2_add(b.c1, b.c2))), v1), v2);
-    Fp2 t1 = fp2_sub(fp2_sub(fp2_mul(fp2_wnorm(fp2_add(a.c0, a.c1)), fp2_wnorm(fp2_add(b.c0, b.c1))), v0), v1);
-    Fp2 t2 = fp2_sub(fp2_sub(fp2_mul(fp2_wnorm(fp2_add(a.c0, a.c2)), fp2_wnorm(fp2_add(b.c0, b.c2))), v0), v2);
-    r.c0 = fp2_vreduce(fp2_add(v0, fp2_mul_nr(t0)));
-    r.c1 = fp2_vreduce(fp2_add(t1, fp2_mul_nr(v2)));
-    r.c2 = fp2_vreduce(fp2_add(t2, v1));
+    Fp2 t0 = fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c1, a.c2), fp2_add(b.c1, b.c2)), v1), v2);
+    Fp2 t1 = fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c0, a.c1), fp2_add(b.c0, b.c1)), v0), v1);
+    Fp2 t2 = fp2_sub(fp2_sub(fp2_mul(fp2_add(a.c0, a.c2), fp2_add(b.c0, b.c2)), v0), v2);
+    r.c0 = fp2_add(v0, fp2_mul_nr(t0));
+    r.c1 = fp2_add(t1, fp2_mul_nr(v2));
+    r.c2 = fp2_add(t2, v1);
 }
 // src/fp6.rs:274-288 ; r may alias a
 ZKP_NOINLINE void fp6_sqr(Fp6 &r, const Fp6 &a) {
     Fp2 s0 = fp2_sqr(a.c0);
     Fp2 ab = fp2_mul(a.c0, a.c1);
     Fp2 s1 = fp2_dbl(ab);
-    Fp2 s2 = fp2_sqr(fp2_wnorm(fp2_add(fp2_sub(a.c0, a.c1), a.c2)));
+    Fp2 s2 = fp2_sqr(fp2_add(fp2_sub(a.c0, a.c1), a.c2));
     Fp2 bc = fp2_mul(a.c1, a.c2);
     Fp2 s3 = fp2_dbl(bc);
     Fp2 s4 = fp2_sqr(a.c2);
-    r.c0 = fp2_vreduce(fp2_add(fp2_mul_nr(s3), s0));
-    r.c1 = fp2_vreduce(fp2_add(fp2_mul_nr(s4), s1));
-    r.c2 = fp2_vreduce(fp2_sub(fp2_sub(fp2_add(fp2_add(s1, s2), s3), s0), s4));
+    r.c0 = fp2_add(fp2_mul_nr(s3), s0);
+    r.c1 = fp2_add(fp2_mul_nr(s4), s1);
+    r.c2 = fp2_sub(fp2_sub(fp2_add(fp2_add(s1, s2), s3), s0), s4);
 }
 // a * (0, c1, 0)  -- src/fp6.rs:102-108 ; r may alias a
 ZKP_NOINLINE void fp6_mul_by_1(Fp6 &r, const Fp6 &a, const Fp2 &c1) {
-    Fp2 t0 = fp2_vreduce(fp2_mul_nr(fp2_mul(a.c2, c1)));
-    Fp2 t1 = fp2_vreduce(fp2_mul(a.c0, c1));
-    Fp2 t2 = fp2_vreduce(fp2_mul(a.c1, c1));
+    Fp2 t0 = fp2_mul_nr(fp2_mul(a.c2, c1));
+    Fp2 t1 = fp2_mul(a.c0, c1);
+    Fp2 t2 = fp2_mul(a.c1, c1);
     r.c0 = t0; r.c1 = t1; r.c2 = t2;
 }
 // a * (c0, c1, 0)  -- src/fp6.rs:110-125 ; r may alias a
@@ -165,20 +156,20 @@ ZKP_NOINLINE void fp6_mul_by_01(Fp6 &r, const Fp6 &a, const Fp2 &c0, const Fp2 &
     Fp2 a_a = fp2_mul(a.c0, c0);
     Fp2 b_b = fp2_mul(a.c1, c1);
     Fp2 t1 = fp2_add(fp2_mul_nr(fp2_mul(a.c2, c1)), a_a);
-    Fp2 t2 = fp2_sub(fp2_sub(fp2_mul(fp2_wnorm(fp2_add(c0, c1)), fp2_wnorm(fp2_add(a.c0, a.c1))), a_a), b_b);
+    Fp2 t2 = fp2_sub(fp2_sub(fp2_mul(fp2_add(c0, c1), fp2_add(a.c0, a.c1)), a_a), b_b);
     Fp2 t3 = fp2_add(fp2_mul(a.c2, c0), b_b);
-    r.c0 = fp2_vreduce(t1); r.c1 = fp2_vreduce(t2); r.c2 = fp2_vreduce(t3);
+    r.c0 = t1; r.c1 = t2; r.c2 = t3;
 }
 // src/fp6.rs:291-309 ; zero maps to zero ; r may alias a
 ZKP_NOINLINE void fp6_inv(Fp6 &r, const Fp6 &a) {
-    Fp2 c0 = fp2_wnorm(fp2_sub(fp2_sqr(a.c0), fp2_mul_nr(fp2_mul(a.c1, a.c2))));
-    Fp2 c1 = fp2_wnorm(fp2_sub(fp2_mul_nr(fp2_sqr(a.c2)), fp2_mul(a.c0, a.c1)));
-    Fp2 c2 = fp2_wnorm(fp2_sub(fp2_sqr(a.c1), fp2_mul(a.c0, a.c2)));
+    Fp2 c0 = fp2_sub(fp2_sqr(a.c0), fp2_mul_nr(fp2_mul(a.c1, a.c2)));
+    Fp2 c1 = fp2_sub(fp2_mul_nr(fp2_sqr(a.c2)), fp2_mul(a.c0, a.c1));
+    Fp2 c2 = fp2_sub(fp2_sqr(a.c1), fp2_mul(a.c0, a.c2));
     Fp2 t = fp2_mul_nr(fp2_add(fp2_mul(a.c1, c2), fp2_mul(a.c2, c1)));
-    t = fp2_inv(fp2_wnorm(fp2_add(t, fp2_mul(a.c0, c0))));
-    r.c0 = fp2_vreduce(fp2_mul(t, c0));
-    r.c1 = fp2_vreduce(fp2_mul(t, c1));
-    r.c2 = fp2_vreduce(fp2_mul(t, c2));
+    t = fp2_inv(fp2_add(t, fp2_mul(a.c0, c0)));
+    r.c0 = fp2_mul(t, c0);
+    r.c1 = fp2_mul(t, c1);
+    r.c2 = fp2_mul(t, c2);
 }
 
 // ------------------------------------------------------------------ Fp12
@@ -194,49 +185,49 @@ ZKP_NOINLINE void fp12_mul(Fp12 &r, const Fp12 &a, const Fp12 &b) {
     fp6_mul(aa, a.c0, b.c0);
     fp6_mul(bb, a.c1, b.c1);
     fp6_add(sa, a.c1, a.c0);
-    fp6_wnorm(sa, sa);
+    
     fp6_add(sb, b.c0, b.c1);
-    fp6_wnorm(sb, sb);
+    
     fp6_mul(sa, sa, sb);
     fp6_sub(sa, sa, aa);
     fp6_sub(sa, sa, bb);
-    fp6_wnorm(r.c1, sa);
+    r.c1 = sa;
     fp6_mul_nr(bb, bb);
     fp6_add(bb, bb, aa);
-    fp6_wnorm(r.c0, bb);
+    r.c0 = bb;
 }
 // complex squaring, 2 Fp6 mul  -- src/fp12.rs:173-184 ; r may alias a
 ZKP_NOINLINE void fp12_sqr(Fp12 &r, const Fp12 &a) {
     Fp6 ab, s, t;
     fp6_mul(ab, a.c0, a.c1);
     fp6_add(s, a.c0, a.c1);
-    fp6_wnorm(s, s);
+    
     fp6_mul_nr(t, a.c1);
     fp6_add(t, t, a.c0);
-    fp6_wnorm(t, t);
+    
     fp6_mul(t, t, s);
     fp6_sub(t, t, ab);
     fp6_add(s, ab, ab);
-    fp6_wnorm(r.c1, s);
+    r.c1 = s;
     fp6_mul_nr(ab, ab);
     fp6_sub(t, t, ab);
-    fp6_wnorm(r.c0, t);
+    r.c0 = t;
 }
 // f * (c0 + c1 v + c4 v w): sparse line multiplication  -- src/fp12.rs:99-111 ; in place
 ZKP_NOINLINE void fp12_mul_by_014(Fp12 &f, const Fp2 &c0, const Fp2 &c1, const Fp2 &c4) {
     Fp6 aa, bb, t;
     fp6_mul_by_01(aa, f.c0, c0, c1);
     fp6_mul_by_1(bb, f.c1, c4);
-    Fp2 o = fp2_wnorm(fp2_add(c1, c4));
+    Fp2 o = fp2_add(c1, c4);
     fp6_add(t, f.c1, f.c0);
-    fp6_wnorm(t, t);
+    
     fp6_mul_by_01(t, t, c0, o);
     fp6_sub(t, t, aa);
     fp6_sub(t, t, bb);
-    fp6_wnorm(f.c1, t);
+    f.c1 = t;
     fp6_mul_nr(bb, bb);
     fp6_add(bb, bb, aa);
-    fp6_wnorm(f.c0, bb);
+    f.c0 = bb;
 }
 // src/fp12.rs:186-190 ; zero maps to zero ; r may alias a
 ZKP_NOINLINE void fp12_inv(Fp12 &r, const Fp12 &a) {
@@ -245,7 +236,7 @@ ZKP_NOINLINE void fp12_inv(Fp12 &r, const Fp12 &a) {
     fp6_sqr(t1, a.c1);
     fp6_mul_nr(t1, t1);
     fp6_sub(t0, t0, t1);
-    fp6_wnorm(t0, t0);
+    
     fp6_inv(t0, t0);
     fp6_mul(r.c0, a.c0, t0);
     fp6_neg(t0, t0);
@@ -258,7 +249,7 @@ ZKP_NOINLINE void fp12_inv(Fp12 &r, const Fp12 &a) {
 ZKP_NOINLINE void fp12_frobenius(Fp12 &r, const Fp12 &a, int k) {
     const Fp2 *src[6] = {&a.c0.c0, &a.c1.c0, &a.c0.c1, &a.c1.c1, &a.c0.c2, &a.c1.c2};
     Fp2 *dst[6] = {&r.c0.c0, &r.c1.c0, &r.c0.c1, &r.c1.c1, &r.c0.c2, &r.c1.c2};
-    const int32_t *tab = ZKP_FROB + (k - 1) * (10 * ZKP_NL);
+    const uint32_t *tab = ZKP_FROB + (k - 1) * (10 * ZKP_NL);
 #pragma unroll 1
     for (int i = 0; i < 6; i++) {
         Fp2 c = *src[i];
@@ -271,23 +262,20 @@ ZKP_NOINLINE void fp12_frobenius(Fp12 &r, const Fp12 &a, int k) {
 }
 
 // Granger-Scott squaring in the cyclotomic subgroup: 9 Fp2 squarings.  r may alias f.
-// The inputs z enter the outputs linearly (z' = 3t -+ 2z), so unlike everywhere else the value is
-// not renewed by a product: fp2_vreduce re-centres the z-carrying term each time, so the value
-// bounds reach a fixed point (|z'| < 8p) across the 63-step chains of cyclotomic_exp.
 ZKP_HD void fp4_square(Fp2 &c0, Fp2 &c1, const Fp2 &a, const Fp2 &b) {
     Fp2 t0 = fp2_sqr(a);
     Fp2 t1 = fp2_sqr(b);
-    c0 = fp2_wnorm(fp2_add(fp2_mul_nr(t1), t0));
-    c1 = fp2_wnorm(fp2_sub(fp2_sub(fp2_sqr(fp2_wnorm(fp2_add(a, b))), t0), t1));
+    c0 = fp2_add(fp2_mul_nr(t1), t0);
+    c1 = fp2_sub(fp2_sub(fp2_sqr(fp2_add(a, b)), t0), t1);
 }
-// 3t - 2z = 2(t - z) + t  and  3t + 2z = 2(t + z) + t, with the z-carrying term value-reduced
+// 3t - 2z = 2(t - z) + t  and  3t + 2z = 2(t + z) + t
 ZKP_HD Fp2 cyc_minus(const Fp2 &t, const Fp2 &z) {
-    Fp2 w = fp2_vreduce(fp2_sub(t, z));
-    return fp2_wnorm(fp2_add(fp2_dbl(w), t));
+    Fp2 w = fp2_sub(t, z);
+    return fp2_add(fp2_dbl(w), t);
 }
 ZKP_HD Fp2 cyc_plus(const Fp2 &t, const Fp2 &z) {
-    Fp2 w = fp2_vreduce(fp2_add(t, z));
-    return fp2_wnorm(fp2_add(fp2_dbl(w), t));
+    Fp2 w = fp2_add(t, z);
+    return fp2_add(fp2_dbl(w), t);
 }
 ZKP_NOINLINE void fp12_cyclotomic_sqr(Fp12 &r, const Fp12 &f) {
     Fp2 t0, t1;
@@ -306,7 +294,7 @@ ZKP_NOINLINE void fp12_cyclotomic_sqr(Fp12 &r, const Fp12 &f) {
         fp4_square(t2, t3, z4, z5);
         r.c0.c1 = cyc_minus(t0, z4);
         r.c1.c2 = cyc_plus(t1, z5);
-        t0 = fp2_wnorm(fp2_mul_nr(t3));
+        t0 = fp2_mul_nr(t3);
         r.c1.c0 = cyc_plus(t0, z2);
         r.c0.c2 = cyc_minus(t2, z3);
     }
