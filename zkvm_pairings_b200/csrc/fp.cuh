@@ -102,8 +102,16 @@ ZKP_HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)(
 // diverge from each other (point generation, infinity handling) without deadlock.
 #ifdef ZKP_DEVICE_BUILD
 ZKP_HD int lane_par() { return (int)(threadIdx.x & 1u); }
+#ifdef ZKP_CONVERGED
+// translation units whose kernels keep all 32 lanes on one path (pairing_kernel.cu): plain SHFL
+ZKP_HD unsigned pair_mask() { return 0xffffffffu; }
+#else
 ZKP_HD unsigned pair_mask() { return 3u << (threadIdx.x & 30u); }
+#endif
 ZKP_HD uint32_t word_xchg(uint32_t v) { return __shfl_xor_sync(pair_mask(), v, 1); }
+// the even (PAR = 0) / odd (PAR = 1) lane's word, in both lanes of the pair
+template <int PAR>
+ZKP_HD uint32_t word_bcast(uint32_t v) { return __shfl_sync(pair_mask(), v, (int)((threadIdx.x & 30u) | PAR)); }
 #else
 // CPU dev simulation: the two lanes are two host threads in lock-step (tests/host_sim/sim.cpp)
 extern thread_local int zkp_sim_par;
@@ -111,6 +119,8 @@ uint32_t zkp_sim_word_xchg(uint32_t v);
 void zkp_sim_xchg(void *buf, unsigned long bytes);
 ZKP_HD int lane_par() { return zkp_sim_par; }
 ZKP_HD uint32_t word_xchg(uint32_t v) { return zkp_sim_word_xchg(v); }
+template <int PAR>
+ZKP_HD uint32_t word_bcast(uint32_t v) { uint32_t o = zkp_sim_word_xchg(v); return zkp_sim_par == PAR ? v : o; }
 #endif
 ZKP_HD bool lane_or(bool x) { return (x | (word_xchg(x ? 1u : 0u) != 0)); }
 ZKP_HD bool lane_and(bool x) { return (x & (word_xchg(x ? 1u : 0u) != 0)); }
@@ -172,13 +182,13 @@ ZKP_HD Fp fp_sub(const Fp &a, const Fp &b) {
     d.l[0] = sub_cc(a.l[0], b.l[0]);
 #pragma unroll
     for (int i = 1; i < ZKP_NL; i++) d.l[i] = subc_cc(a.l[i], b.l[i]);
-    uint32_t mask = subc(0, 0);   // all ones when a < b
-    Fp r;
-    r.l[0] = add_cc(d.l[0], ZKP_2P[0] & mask);
+    if (subc(0, 0) != 0) {   // a < b: add 2p back (a short predicated carry chain, no selects)
+        d.l[0] = add_cc(d.l[0], ZKP_2P[0]);
 #pragma unroll
-    for (int i = 1; i < ZKP_NL - 1; i++) r.l[i] = addc_cc(d.l[i], ZKP_2P[i] & mask);
-    r.l[ZKP_NL - 1] = addc(d.l[ZKP_NL - 1], ZKP_2P[ZKP_NL - 1] & mask);
-    return r;
+        for (int i = 1; i < ZKP_NL - 1; i++) d.l[i] = addc_cc(d.l[i], ZKP_2P[i]);
+        d.l[ZKP_NL - 1] = addc(d.l[ZKP_NL - 1], ZKP_2P[ZKP_NL - 1]);
+    }
+    return d;
 }
 // -a = 2p - a, in [0, 2p]                    -- src/fp.rs:381-405
 ZKP_HD Fp fp_neg(const Fp &a) {
@@ -202,6 +212,20 @@ ZKP_HD Fp fp_xchg(const Fp &a) {
     Fp r = a;
     zkp_sim_xchg(&r, sizeof(Fp));
     return r;
+#endif
+}
+// the value held by the pair's even (PAR = 0) or odd (PAR = 1) lane, delivered to both lanes
+template <int PAR>
+ZKP_HD Fp fp_bcast(const Fp &a) {
+#ifdef ZKP_DEVICE_BUILD
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < ZKP_NL; i++) r.l[i] = word_bcast<PAR>(a.l[i]);
+    return r;
+#else
+    Fp o = a;
+    zkp_sim_xchg(&o, sizeof(Fp));
+    return zkp_sim_par == PAR ? a : o;
 #endif
 }
 // c ? a : b, limb-wise (c is lane-uniform per value, not per limb)

@@ -1,5 +1,9 @@
 // libzkpair.so: CUDA kernels (sm_100a) + the C ABI declared in include/zkpair.h.
 //
+// This translation unit holds the C ABI, the host-side pipeline and the kernels whose lane pairs may
+// diverge from each other (tower ops, products, point generation: pair-masked shuffles).  The
+// pairing kernel itself is pairing_kernel.cu (warp-converged, full-mask shuffles).
+//
 // A LANE PAIR (two adjacent threads) owns one pairing check (k pairs -> shared-accumulator Miller
 // loop -> final exponentiation): every Fp2 of the tower is split over the pair (tower.cuh), so a
 // warp runs 16 independent checks in lock-step (the control flow is data independent) and the
@@ -13,6 +17,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -48,22 +53,6 @@ k_tower_op(int op, const uint64_t *__restrict__ a, const uint64_t *__restrict__ 
         if (status) status[i] = s;
         if ((s & 1) && err) atomicOr(err, 1u);
     }
-}
-
-// mode: bit0 Miller loop, bit1 final exponentiation.  One lane pair per check of k (<= K) pairs.
-template <int K>
-__global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS)
-k_pairing(int mode, const uint64_t *__restrict__ g1, const uint8_t *__restrict__ g1inf,
-          const uint64_t *__restrict__ g2, const uint8_t *__restrict__ g2inf, int k,
-          const uint64_t *__restrict__ in12, uint64_t *__restrict__ out, uint8_t *__restrict__ is_one,
-          uint32_t *err, size_t n) {
-    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
-    if (i >= n) return;
-    size_t e = i * (size_t)k;
-    uint8_t s = pairing_one<K>(mode, g1 ? g1 + 12 * e : nullptr, g1inf ? g1inf + e : nullptr,
-                               g2 ? g2 + 24 * e : nullptr, g2inf ? g2inf + e : nullptr, k,
-                               in12 ? in12 + 72 * i : nullptr, out + 72 * i, is_one ? is_one + i : nullptr);
-    if (s && err && lane_par() == 0) atomicOr(err, 1u);
 }
 
 // out[t] = in[t] * in[t+m] * in[t+2m] * ...   (t < m <= n), canonical limbs in and out
@@ -203,7 +192,10 @@ struct zkp_ctx {
 // two threads (one lane pair) per element
 static inline unsigned grid_for(size_t n) { return (unsigned)((2 * n + ZKP_TPB - 1) / ZKP_TPB); }
 
-static int pair_capacity(int k) { return k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : 8; }
+// k_pairing lives in pairing_kernel.cu (compiled with warp-converged shuffles)
+cudaError_t zkp_launch_k_pairing(int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
+                                 size_t n, int k, const uint64_t *in12, uint64_t *out, uint8_t *is_one, uint32_t *err,
+                                 cudaStream_t st);
 
 static cudaError_t launch_pairing(zkp_ctx *ctx, DevState &d, int mode, const uint64_t *g1, const uint8_t *g1inf,
                                   const uint64_t *g2, const uint8_t *g2inf, size_t n, int k, const uint64_t *in12,
@@ -215,19 +207,13 @@ static cudaError_t launch_pairing(zkp_ctx *ctx, DevState &d, int mode, const uin
         cudaEventCreate(&e1);
         cudaEventRecord(e0, st);
     }
-    dim3 g(grid_for(n)), b(ZKP_TPB);
-    switch (pair_capacity(k)) {
-        case 1: k_pairing<1><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n); break;
-        case 2: k_pairing<2><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n); break;
-        case 4: k_pairing<4><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n); break;
-        default: k_pairing<8><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n); break;
-    }
+    cudaError_t rc = zkp_launch_k_pairing(mode, g1, g1inf, g2, g2inf, n, k, in12, out, is_one, err, st);
     ctx->launches++;
     if (ctx->timing) {
         cudaEventRecord(e1, st);
         d.timers.emplace_back(e0, e1);
     }
-    return cudaGetLastError();
+    return rc;
 }
 
 // product of n canonical Fp12 at d_in -> d_out (1 element).  scratch: zkp_product_scratch_elems(n)

@@ -50,12 +50,14 @@ ZKP_NOINLINE Fp load_fp(const uint64_t *src, bool &bad) {
 }
 // Montgomery Fp -> canonical u64 limbs; returns the OR of all output words except the lowest and
 // writes the lowest to *low (so callers can test for 0 / 1 without another conversion)
-ZKP_NOINLINE uint32_t store_fp(uint64_t *dst, Fp m, uint32_t *low) {
+ZKP_NOINLINE uint32_t store_fp(uint64_t *dst, Fp m, uint32_t *low, bool live = true) {
     uint32_t w[12];
     fp_to_words(w, m);
     uint32_t rest = 0;
+    if (live) {
 #pragma unroll
-    for (int i = 0; i < 6; i++) dst[i] = (uint64_t)w[2 * i] | ((uint64_t)w[2 * i + 1] << 32);
+        for (int i = 0; i < 6; i++) dst[i] = (uint64_t)w[2 * i] | ((uint64_t)w[2 * i + 1] << 32);
+    }
 #pragma unroll
     for (int i = 1; i < 12; i++) rest |= w[i];
     if (low) *low = w[0];
@@ -63,7 +65,7 @@ ZKP_NOINLINE uint32_t store_fp(uint64_t *dst, Fp m, uint32_t *low) {
 }
 // Lane-split marshalling: an Fp2 occupies 12 u64 (c0 | c1); the even lane moves c0, the odd lane c1.
 ZKP_HD Fp2 load_fp2(const uint64_t *src, bool &bad) { Fp2 r; r.c = load_fp(src + 6 * lane_par(), bad); return r; }
-ZKP_HD uint32_t store_fp2(uint64_t *dst, const Fp2 &a, uint32_t *low) { return store_fp(dst + 6 * lane_par(), a.c, low); }
+ZKP_HD uint32_t store_fp2(uint64_t *dst, const Fp2 &a, uint32_t *low, bool live = true) { return store_fp(dst + 6 * lane_par(), a.c, low, live); }
 ZKP_HD void load_fp2s(Fp2 *dst, const uint64_t *src, int n, bool &bad) {
     for (int i = 0; i < n; i++) dst[i] = load_fp2(src + 12 * i, bad);
 }
@@ -147,14 +149,14 @@ ZKP_HD uint8_t tower_op_one(int op, const uint64_t *a, const uint64_t *b, uint64
 ZKP_HD void load_g1(G1A &p, const uint64_t *xy, bool &bad) { p.x = load_fp(xy, bad); p.y = load_fp(xy + 6, bad); }
 ZKP_HD void load_g2(G2A &q, const uint64_t *xy, bool &bad) { q.x = load_fp2(xy, bad); q.y = load_fp2(xy + 12, bad); }
 // stores f and returns true (in both lanes) when it equals Fp12::one() (canonical 1, 0, ..., 0)
-ZKP_HD bool store_fp12(uint64_t *dst, const Fp12 &f) {
+ZKP_HD bool store_fp12(uint64_t *dst, const Fp12 &f, bool live = true) {
     const Fp2 *c = &f.c0.c0;
     uint32_t low = 0, rest = 0;
-    rest |= store_fp2(dst, c[0], &low);
+    rest |= store_fp2(dst, c[0], &low, live);
     bool first = lane_par() == 0 ? (low == 1u) : (low == 0u);
     for (int i = 1; i < 6; i++) {
         uint32_t l2 = 0;
-        rest |= store_fp2(dst + 12 * i, c[i], &l2);
+        rest |= store_fp2(dst + 12 * i, c[i], &l2, live);
         rest |= l2;
     }
     return lane_and(first & (rest == 0));
@@ -165,12 +167,13 @@ ZKP_HD void load_fp12(Fp12 &f, const uint64_t *src, bool &bad) { load_fp2s(&f.c0
 enum { ZKP_DO_MILLER = 1, ZKP_DO_FINAL_EXP = 2 };
 
 // One "check": k pairs -> shared-accumulator Miller loop (-> final exponentiation).  g1/g2/inf
-// point at this check's first pair.  Returns status bit0 = non-canonical input.
+// point at this check's first pair.  Returns status bit0 = non-canonical input.  Control flow is
+// lane-uniform (k and mode are kernel arguments); `live` = false suppresses the stores only.
 // is_one (optional) receives 1 when the result equals Fp12::one().  K = compile-time capacity
 // (k <= K) so the per-thread scratch is sized for the common k = 1 case.
 template <int K>
 ZKP_HD uint8_t pairing_one(int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
-                           int k, const uint64_t *in12, uint64_t *out, uint8_t *is_one) {
+                           int k, const uint64_t *in12, uint64_t *out, uint8_t *is_one, bool live = true) {
     bool bad = false;
     Fp12 f;
     if (mode & ZKP_DO_MILLER) {
@@ -188,8 +191,8 @@ ZKP_HD uint8_t pairing_one(int mode, const uint64_t *g1, const uint8_t *g1inf, c
         load_fp12(f, in12, bad);
     }
     if (mode & ZKP_DO_FINAL_EXP) final_exponentiation(f, f);
-    bool one = store_fp12(out, f);
-    if (is_one && lane_par() == 0) *is_one = one ? 1 : 0;
+    bool one = store_fp12(out, f, live);
+    if (is_one && live && lane_par() == 0) *is_one = one ? 1 : 0;
     return lane_or(bad) ? 1 : 0;
 }
 

@@ -65,11 +65,14 @@ ZKP_NOINLINE void addition_step(G2P &r, const G2A &q, Fp2 *co) {
     co[1] = fp2_dbl(fp2_neg(t6));
 }
 
-// SURVEY 9.1 ell: scale the line by P and fold it into f
-ZKP_HD void ell(Fp12 &f, const Fp2 *co, const G1A &p) {
-    Fp2 a = fp2_mul_fp(co[0], p.y);
-    Fp2 b = fp2_mul_fp(co[1], p.x);
-    fp12_mul_by_014(f, co[2], b, a);
+// SURVEY 9.1 ell: scale the line by P and fold it into f.  A pair flagged `skip` (a point at
+// infinity) multiplies f by the line (1, 0, 0) = one instead -- by selects, not by a branch, so all
+// lanes of a warp stay on one path.
+ZKP_HD Fp2 fp2_select(bool c, const Fp2 &a, const Fp2 &b) { Fp2 r; r.c = fp_select(c, a.c, b.c); return r; }
+ZKP_HD void ell(Fp12 &f, const Fp2 *co, const G1A &p, bool skip) {
+    Fp2 a = fp2_select(skip, fp2_zero(), fp2_mul_fp(co[0], p.y));
+    Fp2 b = fp2_select(skip, fp2_zero(), fp2_mul_fp(co[1], p.x));
+    fp12_mul_by_014(f, fp2_select(skip, fp2_one(), co[2]), b, a);
 }
 
 // Bits of |x| >> 1 below its leading one (bit 62), MSB first: 62 iterations, additions where set.
@@ -89,23 +92,20 @@ ZKP_HD void miller_loop(Fp12 &f, const G1A *ps, const G2A *qs, const bool *skip,
     for (int b = 61; b >= 0; b--) {
         bool bit = (ZKP_X_HALF >> b) & 1;
         for (int j = 0; j < k; j++) {
-            if (skip[j]) continue;
             doubling_step(rs[j], co);
-            ell(f, co, ps[j]);
+            ell(f, co, ps[j], skip[j]);
         }
         if (bit) {
             for (int j = 0; j < k; j++) {
-                if (skip[j]) continue;
                 addition_step(rs[j], qs[j], co);
-                ell(f, co, ps[j]);
+                ell(f, co, ps[j], skip[j]);
             }
         }
         fp12_sqr(f, f);
     }
     for (int j = 0; j < k; j++) {
-        if (skip[j]) continue;
         doubling_step(rs[j], co);
-        ell(f, co, ps[j]);
+        ell(f, co, ps[j], skip[j]);
     }
     fp12_conj(f, f);
 }
