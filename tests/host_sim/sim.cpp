@@ -19,6 +19,8 @@
 
 namespace zkp {
 thread_local int zkp_sim_par = 0;
+thread_local unsigned long long zkp_sim_macs = 0;
+static std::atomic<unsigned long long> g_macs{0};
 static std::atomic<int> g_arrived{0};
 static std::atomic<int> g_phase{0};
 static unsigned char g_slot[2][512];
@@ -52,10 +54,14 @@ template <class F>
 static void run_pair(F f) {
     std::thread odd([&]() {
         zkp_sim_par = 1;
+        zkp_sim_macs = 0;
         f();
+        g_macs += zkp_sim_macs;
     });
     zkp_sim_par = 0;
+    zkp_sim_macs = 0;
     f();
+    g_macs += zkp_sim_macs;
     odd.join();
 }
 
@@ -85,6 +91,8 @@ int sim_pairing(int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64
     });
     return bad.load() ? -1 : 0;
 }
+// wide MACs executed by both lanes since the last call (boundary conversions included)
+uint64_t sim_take_mac_count() { return g_macs.exchange(0); }
 uint64_t sim_splitmix64_at(uint64_t seed, uint64_t idx) { return splitmix64_at(seed, idx); }
 void sim_gen_points(const uint64_t *k1, const uint64_t *k2, size_t n, uint64_t *g1, uint8_t *g1inf, uint64_t *g2, uint8_t *g2inf) {
     run_pair([&]() {

@@ -195,6 +195,24 @@ def test_sim_point_generator_matches_oracle(sim, coracle):
     assert coracle.group_op("g2", "torsion_free", g2[0]) and coracle.group_op("g1", "torsion_free", g1[0])
 
 
+def test_sim_executed_mac_count(sim, coracle):
+    """Work accounting behind bench.py's `executed_macs_per_pairing`: the dev simulation counts the
+    32x32->64 MACs both lanes issue (300 per Montgomery product, 444 per two-product form)."""
+    sim.sim_take_mac_count.restype = ctypes.c_uint64
+    g1, _, g2, _ = util.oracle_points(coracle, 0x5EED, 0, 4)
+    out, ml = np.zeros((1, 72), np.uint64), np.zeros((1, 72), np.uint64)
+    sim.sim_take_mac_count()
+    sim.sim_pairing(1, _p(g1), None, _p(g2), None, ctypes.c_size_t(1), 1, None, _p(ml), None)
+    miller = sim.sim_take_mac_count()
+    sim.sim_pairing(2, None, None, None, None, ctypes.c_size_t(1), 1, _p(ml), _p(out), None)
+    fexp = sim.sim_take_mac_count()
+    sim.sim_pairing(3, _p(g1), None, _p(g2), None, ctypes.c_size_t(1), 4, None, _p(out), None)
+    check4 = sim.sim_take_mac_count()
+    assert (miller, fexp, check4) == (2052576, 2714568, 8942856)
+    sys_path = os.path.join(ROOT, "bench.py")
+    assert "4_767_144" in open(sys_path).read() and miller + fexp == 4767144
+
+
 def test_sim_operand_bounds_are_asserted(sim):
     """The dev simulation aborts (ZKP_SIM_ASSERT) when a Montgomery product is handed an operand
     above the bound fp.cuh documents; every other sim test therefore also proves that no call site

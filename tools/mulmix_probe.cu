@@ -17,8 +17,12 @@ using namespace zkp;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
 
 template <int ADDS>
-__global__ void __launch_bounds__(128) k_mix(uint32_t *sink, int iters) {
+__global__ void __launch_bounds__(128) k_mix(uint32_t *sink, int iters, int delay, int sms) {
     extern __shared__ uint8_t dyn[];
+    if (delay > 0 && ((blockIdx.x / sms) & 1)) {   // de-phase every second co-resident block
+        long long t0 = clock64();
+        while (clock64() - t0 < delay) {}
+    }
     Fp2 x, y;
 #pragma unroll
     for (int i = 0; i < ZKP_NL; i++) {
@@ -61,7 +65,7 @@ static void run(const char *name, F launch, int wps, double macs_per_thread, int
         if (ms < best) best = ms;
     }
     double total = macs_per_thread * 128.0 * blocks / (best * 1e-3);
-    printf("%-18s warps/smsp=%d  %.3f ms  %.2f T wide-MAC/s\n", name, wps, best, total / 1e12);
+    printf("%-22s warps/smsp=%d  %.3f ms  %.2f T wide-MAC/s\n", name, wps, best, total / 1e12);
     fflush(stdout);
     cudaFree(sink);
 }
@@ -73,11 +77,19 @@ int main() {
     CK(cudaFuncSetAttribute(k_mix<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_mix<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const int iters = 2000;
-    int ws[] = {1, 2, 3, 4, 5, 6, 8};
+    int ws[] = {1, 2, 3, 4, 6, 8};
+    int delays[] = {0, 1500, 3000};
     for (int w : ws) {
-        run("mul+sqr only", [&](int b, size_t s, uint32_t *k) { k_mix<0><<<b, 128, s>>>(k, iters); }, w, iters * 744.0, sms);
-        run("mul+sqr+6 adds", [&](int b, size_t s, uint32_t *k) { k_mix<1><<<b, 128, s>>>(k, iters); }, w, iters * 744.0, sms);
-        run("mul+sqr+10 adds", [&](int b, size_t s, uint32_t *k) { k_mix<2><<<b, 128, s>>>(k, iters); }, w, iters * 744.0, sms);
+        for (int d : delays) {
+            if (w == 1 && d) continue;
+            char name[64];
+            snprintf(name, sizeof name, "mul+sqr      d=%d", d);
+            run(name, [&](int b, size_t s, uint32_t *k) { k_mix<0><<<b, 128, s>>>(k, iters, d, sms); }, w, iters * 744.0, sms);
+            snprintf(name, sizeof name, "mul+sqr+6add d=%d", d);
+            run(name, [&](int b, size_t s, uint32_t *k) { k_mix<1><<<b, 128, s>>>(k, iters, d, sms); }, w, iters * 744.0, sms);
+            snprintf(name, sizeof name, "mul+sqr+10ad d=%d", d);
+            run(name, [&](int b, size_t s, uint32_t *k) { k_mix<2><<<b, 128, s>>>(k, iters, d, sms); }, w, iters * 744.0, sms);
+        }
     }
     return 0;
 }

@@ -115,6 +115,7 @@ ZKP_HD uint32_t word_bcast(uint32_t v) { return __shfl_sync(pair_mask(), v, (int
 #else
 // CPU dev simulation: the two lanes are two host threads in lock-step (tests/host_sim/sim.cpp)
 extern thread_local int zkp_sim_par;
+extern thread_local unsigned long long zkp_sim_macs;   // wide MACs issued by this simulated lane (work accounting)
 uint32_t zkp_sim_word_xchg(uint32_t v);
 void zkp_sim_xchg(void *buf, unsigned long bytes);
 ZKP_HD int lane_par() { return zkp_sim_par; }
@@ -325,6 +326,7 @@ ZKP_HD Fp mont_mul(const Fp &a, const uint32_t *b) {
 }
 ZKP_HD Fp mont_mul(const Fp &a, const Fp &b) {
 #ifndef ZKP_DEVICE_BUILD
+    zkp_sim_macs += 300;
     ZKP_SIM_ASSERT((fp_leq_2p(a) && fp_leq_4p(b)) || (fp_leq_4p(a) && fp_leq_2p(b)), "mont_mul operand bound");
 #endif
     return mont_mul(a, b.l);
@@ -333,6 +335,7 @@ ZKP_HD Fp mont_mul(const Fp &a, const Fp &b) {
 // MACs.  This is one lane's half of an Fp2 product.  All four operands <= 2p.
 ZKP_HD Fp mont_mul2(const Fp &u, const Fp &v, const Fp &w, const Fp &z) {
 #ifndef ZKP_DEVICE_BUILD
+    zkp_sim_macs += 444;
     ZKP_SIM_ASSERT(fp_leq_2p(u) && fp_leq_2p(v) && fp_leq_2p(w) && fp_leq_2p(z), "mont_mul2 operand bound");
 #endif
     uint32_t ev[ZKP_NL], od[ZKP_NL];
