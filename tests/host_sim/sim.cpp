@@ -91,6 +91,18 @@ int sim_pairing(int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64
     });
     return bad.load() ? -1 : 0;
 }
+// Montgomery-trick batch inversion of pairing.cuh (one simulated thread, runs of `run` elements)
+void sim_batch_inv(const uint64_t *in, uint64_t *out, size_t n, int run) {
+    zkp_sim_par = 0;
+    bool bad = false;
+    for (size_t lo = 0; lo < n; lo += run) {
+        int cnt = (int)(n - lo < (size_t)run ? n - lo : run);
+        Fp v[64], pre[64];
+        for (int i = 0; i < cnt; i++) v[i] = load_fp(in + 6 * (lo + i), bad);
+        fp_batch_inv(v, pre, cnt);
+        for (int i = 0; i < cnt; i++) store_fp(out + 6 * (lo + i), v[i], nullptr);
+    }
+}
 // wide MACs executed by both lanes since the last call (boundary conversions included)
 uint64_t sim_take_mac_count() { return g_macs.exchange(0); }
 uint64_t sim_splitmix64_at(uint64_t seed, uint64_t idx) { return splitmix64_at(seed, idx); }

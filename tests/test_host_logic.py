@@ -195,6 +195,22 @@ def test_sim_point_generator_matches_oracle(sim, coracle):
     assert coracle.group_op("g2", "torsion_free", g2[0]) and coracle.group_op("g1", "torsion_free", g1[0])
 
 
+def test_sim_batch_inversion(sim, coracle, pyref):
+    """fp_batch_inv (Montgomery's trick, used between the two final-exponentiation launches): equal to
+    element-wise Fermat inversion, zeros stay zero and do not poison their run, ragged last run."""
+    n = 37
+    a = util.random_fp_matrix(n, 1, seed=77)
+    a[0] = 0
+    a[5] = 0
+    a[16] = util.fp_arr([1]).reshape(-1, 6)[0]
+    a[36] = util.fp_arr([pyref.P - 1]).reshape(-1, 6)[0]
+    out = np.zeros_like(a)
+    sim.sim_batch_inv(_p(a), _p(out), ctypes.c_size_t(n), 16)
+    vals = util.arr_fp(a)
+    assert util.arr_fp(out) == [pow(v, pyref.P - 2, pyref.P) for v in vals]
+    assert util.arr_fp(out)[0] == 0 and util.arr_fp(out)[16] == 1
+
+
 def test_sim_executed_mac_count(sim, coracle):
     """Work accounting behind bench.py's `executed_macs_per_pairing`: the dev simulation counts the
     32x32->64 MACs both lanes issue (300 per Montgomery product, 444 per two-product form)."""

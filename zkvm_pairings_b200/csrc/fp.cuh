@@ -386,14 +386,16 @@ ZKP_HD void fp_to_words(uint32_t *w, const Fp &m) {
 #pragma unroll
     for (int i = 0; i < ZKP_NL; i++) w[i] = lt ? t.l[i] : d.l[i];
 }
-// Comparisons go through the canonical form (rare: flags and degenerate cases of the group law).
+// value == 0 mod p for a 2p-redundant value: the only representatives are 0, p and 2p
 ZKP_HD bool fp_is_zero(const Fp &a) {
-    uint32_t w[ZKP_NL];
-    fp_to_words(w, a);
-    uint32_t t = 0;
+    uint32_t z = 0, zp = 0, z2 = 0;
 #pragma unroll
-    for (int i = 0; i < ZKP_NL; i++) t |= w[i];
-    return t == 0;
+    for (int i = 0; i < ZKP_NL; i++) {
+        z |= a.l[i];
+        zp |= a.l[i] ^ ZKP_P[i];
+        z2 |= a.l[i] ^ ZKP_2P[i];
+    }
+    return (z == 0) | (zp == 0) | (z2 == 0);
 }
 
 }  // namespace zkp

@@ -192,10 +192,11 @@ struct zkp_ctx {
 // two threads (one lane pair) per element
 static inline unsigned grid_for(size_t n) { return (unsigned)((2 * n + ZKP_TPB - 1) / ZKP_TPB); }
 
-// k_pairing lives in pairing_kernel.cu (compiled with warp-converged shuffles)
+// the pairing kernels live in pairing_kernel.cu (compiled with warp-converged shuffles)
+extern "C" size_t zkp_fe_scratch_bytes(size_t n);
 cudaError_t zkp_launch_k_pairing(int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
                                  size_t n, int k, const uint64_t *in12, uint64_t *out, uint8_t *is_one, uint32_t *err,
-                                 cudaStream_t st);
+                                 void *scratch, cudaStream_t st, int *launches);
 
 static cudaError_t launch_pairing(zkp_ctx *ctx, DevState &d, int mode, const uint64_t *g1, const uint8_t *g1inf,
                                   const uint64_t *g2, const uint8_t *g2inf, size_t n, int k, const uint64_t *in12,
@@ -207,8 +208,16 @@ static cudaError_t launch_pairing(zkp_ctx *ctx, DevState &d, int mode, const uin
         cudaEventCreate(&e1);
         cudaEventRecord(e0, st);
     }
-    cudaError_t rc = zkp_launch_k_pairing(mode, g1, g1inf, g2, g2inf, n, k, in12, out, is_one, err, st);
-    ctx->launches++;
+    // the final exponentiation parks its state between launches in stream-ordered scratch memory
+    void *scratch = nullptr;
+    if (mode & 2) {
+        cudaError_t e = cudaMallocAsync(&scratch, zkp_fe_scratch_bytes(n), st);
+        if (e != cudaSuccess) return e;
+    }
+    int nl = 0;
+    cudaError_t rc = zkp_launch_k_pairing(mode, g1, g1inf, g2, g2inf, n, k, in12, out, is_one, err, scratch, st, &nl);
+    ctx->launches += nl;
+    if (scratch) cudaFreeAsync(scratch, st);
     if (ctx->timing) {
         cudaEventRecord(e1, st);
         d.timers.emplace_back(e0, e1);

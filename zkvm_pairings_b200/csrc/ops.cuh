@@ -172,10 +172,8 @@ enum { ZKP_DO_MILLER = 1, ZKP_DO_FINAL_EXP = 2 };
 // is_one (optional) receives 1 when the result equals Fp12::one().  K = compile-time capacity
 // (k <= K) so the per-thread scratch is sized for the common k = 1 case.
 template <int K>
-ZKP_HD uint8_t pairing_one(int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
-                           int k, const uint64_t *in12, uint64_t *out, uint8_t *is_one, bool live = true) {
-    bool bad = false;
-    Fp12 f;
+ZKP_HD void pairing_front(Fp12 &f, bool &bad, int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2,
+                          const uint8_t *g2inf, int k, const uint64_t *in12) {
     if (mode & ZKP_DO_MILLER) {
         G1A ps[K];
         G2A qs[K];
@@ -190,6 +188,15 @@ ZKP_HD uint8_t pairing_one(int mode, const uint64_t *g1, const uint8_t *g1inf, c
     } else {
         load_fp12(f, in12, bad);
     }
+}
+// the whole check in one call (dev simulation and small helpers; the GPU path splits the final
+// exponentiation over three launches, pairing_kernel.cu)
+template <int K>
+ZKP_HD uint8_t pairing_one(int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
+                           int k, const uint64_t *in12, uint64_t *out, uint8_t *is_one, bool live = true) {
+    bool bad = false;
+    Fp12 f;
+    pairing_front<K>(f, bad, mode, g1, g1inf, g2, g2inf, k, in12);
     if (mode & ZKP_DO_FINAL_EXP) final_exponentiation(f, f);
     bool one = store_fp12(out, f, live);
     if (is_one && live && lane_par() == 0) *is_one = one ? 1 : 0;

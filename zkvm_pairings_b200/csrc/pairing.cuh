@@ -121,11 +121,20 @@ ZKP_NOINLINE void cyclotomic_exp(Fp12 &r, const Fp12 &f) {
     fp12_conj(r, t);
 }
 
-// SURVEY 9.2.  f must be non-zero (a Miller-loop output always is); zero maps to zero.
-ZKP_HD void final_exponentiation(Fp12 &r, const Fp12 &f) {
+// SURVEY 9.2, split around the single Fp inversion of the easy part (f^-1): fe_prepare leaves the
+// cofactors and the norm n, fe_finish continues from ninv = 1/n.  The pairing kernels run the two
+// halves as separate launches with a batched inversion kernel in between (Montgomery's trick across
+// pairings: ~41 Fp products per inverse instead of a 609-product Fermat ladder per lane).
+// f must be non-zero (a Miller-loop output always is); zero maps to zero.
+struct FeState {
+    Fp6 c;   // cofactors of the Fp6 inverse
+    Fp2 t;   // the Fp2 whose norm is inverted
+};
+ZKP_HD Fp fe_prepare(FeState &s, const Fp12 &f) { return fp12_inv_prepare(s.c, s.t, f); }
+ZKP_HD void fe_finish(Fp12 &r, const Fp12 &f, const FeState &s, const Fp &ninv) {
     Fp12 t0, t1, t2, t3, t4, t5, t6;
     fp12_conj(t0, f);                 // f^(p^6)
-    fp12_inv(t1, f);
+    fp12_inv_finish(t1, f, s.c, s.t, ninv);
     fp12_mul(t2, t0, t1);             // f^(p^6-1)
     t1 = t2;
     fp12_frobenius(t2, t2, 2);
@@ -153,6 +162,29 @@ ZKP_HD void final_exponentiation(Fp12 &r, const Fp12 &f) {
     fp12_mul(t3, t3, t1);
     fp12_mul(t3, t3, t6);
     fp12_mul(r, t3, t4);
+}
+ZKP_HD void final_exponentiation(Fp12 &r, const Fp12 &f) {
+    FeState s;
+    Fp n = fe_prepare(s, f);
+    fe_finish(r, f, s, fp_inv(n));
+}
+
+// Montgomery's trick over a run of values held by ONE thread: v[i] <- 1/v[i] for i < cnt with a
+// single Fermat inversion and 3 (cnt - 1) products.  Zeros (a zero norm: only for a zero Fp12
+// input, which maps to zero) are skipped and stay zero.  `pre` is scratch of cnt elements.
+ZKP_HD void fp_batch_inv(Fp *v, Fp *pre, int cnt) {
+    Fp acc = fp_one();
+    for (int i = 0; i < cnt; i++) {
+        pre[i] = acc;
+        if (!fp_is_zero(v[i])) acc = fmul(acc, v[i]);
+    }
+    acc = fp_inv(acc);
+    for (int i = cnt - 1; i >= 0; i--) {
+        if (fp_is_zero(v[i])) continue;
+        Fp inv = fmul(acc, pre[i]);
+        acc = fmul(acc, v[i]);
+        v[i] = inv;
+    }
 }
 
 // ------------------------------------------------------------------ group helpers (input prep)

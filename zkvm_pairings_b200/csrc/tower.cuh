@@ -101,15 +101,20 @@ ZKP_NOINLINE Fp2 fp2_sqr(Fp2 a) {
     return r;
 }
 ZKP_HD Fp2 fp2_mul_fp(const Fp2 &a, const Fp &k) { Fp2 r; r.c = fmul(a.c, k); return r; }   // src/fp2.rs:95-102
-// src/fp2.rs:278-296 ; zero maps to zero.  Both lanes run the Fermat inversion of the norm.
-ZKP_HD Fp2 fp2_inv(const Fp2 &a) {
+// src/fp2.rs:278-296 ; zero maps to zero.  Split around the Fp inversion of the norm so that the
+// pairing kernels can batch that inversion over many pairings (pairing_kernel.cu):
+//   n = a0^2 + a1^2 (both lanes)   ->   ninv = 1/n   ->   (a0 * ninv, -a1 * ninv)
+ZKP_HD Fp fp2_norm(const Fp2 &a) {
     Fp n = fsqr(a.c);
-    Fp t = fp_inv(fp_add(n, fp_xchg(n)));
-    Fp m = fmul(a.c, t);
+    return fp_add(n, fp_xchg(n));
+}
+ZKP_HD Fp2 fp2_inv_finish(const Fp2 &a, const Fp &ninv) {
+    Fp m = fmul(a.c, ninv);
     Fp2 r;
     r.c = fp_select(lane_par() != 0, fp_neg(m), m);
     return r;
 }
+ZKP_HD Fp2 fp2_inv(const Fp2 &a) { return fp2_inv_finish(a, fp_inv(fp2_norm(a))); }
 
 // ------------------------------------------------------------------ Fp6
 struct Fp6 {
@@ -168,16 +173,26 @@ ZKP_NOINLINE void fp6_mul_by_01(Fp6 &r, const Fp6 &a, const Fp2 &c0, const Fp2 &
     Fp2 t3 = fp2_add(fp2_mul(a.c2, c0), b_b);
     r.c0 = t1; r.c1 = t2; r.c2 = t3;
 }
-// src/fp6.rs:291-309 ; zero maps to zero ; r may alias a
-ZKP_NOINLINE void fp6_inv(Fp6 &r, const Fp6 &a) {
+// src/fp6.rs:291-309 ; zero maps to zero ; r may alias a.  Split like fp2_inv: `c` receives the three
+// cofactors, the return value is the Fp2 whose inverse scales them.
+ZKP_NOINLINE Fp2 fp6_inv_prepare(Fp6 &c, const Fp6 &a) {
     Fp2 c0 = fp2_sub(fp2_sqr(a.c0), fp2_mul_nr(fp2_mul(a.c1, a.c2)));
     Fp2 c1 = fp2_sub(fp2_mul_nr(fp2_sqr(a.c2)), fp2_mul(a.c0, a.c1));
     Fp2 c2 = fp2_sub(fp2_sqr(a.c1), fp2_mul(a.c0, a.c2));
     Fp2 t = fp2_mul_nr(fp2_add(fp2_mul(a.c1, c2), fp2_mul(a.c2, c1)));
-    t = fp2_inv(fp2_add(t, fp2_mul(a.c0, c0)));
-    r.c0 = fp2_mul(t, c0);
-    r.c1 = fp2_mul(t, c1);
-    r.c2 = fp2_mul(t, c2);
+    t = fp2_add(t, fp2_mul(a.c0, c0));
+    c.c0 = c0; c.c1 = c1; c.c2 = c2;
+    return t;
+}
+ZKP_NOINLINE void fp6_inv_finish(Fp6 &r, const Fp6 &c, const Fp2 &tinv) {
+    r.c0 = fp2_mul(tinv, c.c0);
+    r.c1 = fp2_mul(tinv, c.c1);
+    r.c2 = fp2_mul(tinv, c.c2);
+}
+ZKP_HD void fp6_inv(Fp6 &r, const Fp6 &a) {
+    Fp6 c;
+    Fp2 t = fp6_inv_prepare(c, a);
+    fp6_inv_finish(r, c, fp2_inv(t));
 }
 
 // ------------------------------------------------------------------ Fp12
@@ -237,18 +252,30 @@ ZKP_NOINLINE void fp12_mul_by_014(Fp12 &f, const Fp2 &c0, const Fp2 &c1, const F
     fp6_add(bb, bb, aa);
     f.c0 = bb;
 }
-// src/fp12.rs:186-190 ; zero maps to zero ; r may alias a
-ZKP_NOINLINE void fp12_inv(Fp12 &r, const Fp12 &a) {
+// src/fp12.rs:186-190 ; zero maps to zero ; r may alias a.  Split around the one Fp inversion:
+//   prepare: c = cofactors of (a.c0^2 - v a.c1^2)^-1, t = the Fp2 to invert, returns n = norm(t)
+//   finish : given ninv = 1/n, r = a^-1
+ZKP_NOINLINE Fp fp12_inv_prepare(Fp6 &c, Fp2 &t, const Fp12 &a) {
     Fp6 t0, t1;
     fp6_sqr(t0, a.c0);
     fp6_sqr(t1, a.c1);
     fp6_mul_nr(t1, t1);
     fp6_sub(t0, t0, t1);
-    
-    fp6_inv(t0, t0);
+    t = fp6_inv_prepare(c, t0);
+    return fp2_norm(t);
+}
+ZKP_NOINLINE void fp12_inv_finish(Fp12 &r, const Fp12 &a, const Fp6 &c, const Fp2 &t, const Fp &ninv) {
+    Fp6 t0;
+    fp6_inv_finish(t0, c, fp2_inv_finish(t, ninv));
     fp6_mul(r.c0, a.c0, t0);
     fp6_neg(t0, t0);
     fp6_mul(r.c1, a.c1, t0);
+}
+ZKP_HD void fp12_inv(Fp12 &r, const Fp12 &a) {
+    Fp6 c;
+    Fp2 t;
+    Fp n = fp12_inv_prepare(c, t, a);
+    fp12_inv_finish(r, a, c, t, fp_inv(n));
 }
 // f^(p^k), k = 1..3, with the TRUE coefficients gamma_{k,i} = xi^(i (p^k-1)/6) on the w-power
 // basis (c0.c0, c1.c0, c0.c1, c1.c1, c0.c2, c1.c2 <-> w^0..w^5).  The reference's
