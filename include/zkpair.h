@@ -171,6 +171,28 @@ int32_t zkp_gen_points_dev(zkp_ctx *ctx, int32_t dev, uint64_t seed, uint64_t fi
 int32_t zkp_gen_points(zkp_ctx *ctx, uint64_t seed, uint64_t first, size_t n, uint64_t *g1_xy,
                        uint8_t *g1_inf, uint64_t *g2_xy, uint8_t *g2_inf);
 
+/* ---- group-level batch operations (the callers either side of a pairing) ------------ */
+
+/* status byte per point */
+#define ZKP_POINT_OK 0                 /* G1Affine::is_valid / G2Affine::is_valid == Ok(())            */
+#define ZKP_POINT_NOT_ON_CURVE 1       /* Err("Point is not on curve")        src/g1.rs:54, src/g2.rs:61 */
+#define ZKP_POINT_NOT_TORSION_FREE 2   /* Err("Point is not torsion free")    src/g1.rs:57, src/g2.rs:64 */
+
+/* G1Affine::is_valid (src/g1.rs:49-62): identity -> ok; y^2 = x^3 + 4 (src/g1.rs:95-101); subgroup test
+ * -[x^2]P == (beta x, y) (src/g1.rs:103-115).  g1_inf may be NULL. */
+int32_t zkp_g1_check_batch(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_inf, size_t n, uint8_t *status);
+/* G2Affine::is_valid (src/g2.rs:57-69): y^2 = x^3 + 4(1+u) (src/g2.rs:109-120); psi(Q) == -[|x|]Q
+ * (src/g2.rs:126-170). */
+int32_t zkp_g2_check_batch(zkp_ctx *ctx, const uint64_t *g2_xy, const uint8_t *g2_inf, size_t n, uint8_t *status);
+/* [k_i]P_i, k_i = 4 little-endian u64 (the limbs of an Fr, src/fr.rs): `&G1Affine * &Fr` (src/g1.rs:130-153)
+ * and `&G2Affine * &Fr` (src/g2.rs:185-208) as the correct double-and-add over all 256 bits (the reference's
+ * G1 loop drops bit 0 of the scalar, src/g1.rs:138-142 -- deliberately not reproduced).  Results are affine;
+ * the identity is (0, 1) with out_inf = 1 (src/g1.rs:25-31). */
+int32_t zkp_g1_mul_batch(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_inf, const uint64_t *scalars,
+                         size_t n, uint64_t *out_xy, uint8_t *out_inf);
+int32_t zkp_g2_mul_batch(zkp_ctx *ctx, const uint64_t *g2_xy, const uint8_t *g2_inf, const uint64_t *scalars,
+                         size_t n, uint64_t *out_xy, uint8_t *out_inf);
+
 /* ---- measurement helpers -------------------------------------------------------------------- */
 
 /* Integer-multiply roofline probe: runs independent IMAD.WIDE.U32 (kind 0), IMAD lo (kind 1) or

@@ -91,6 +91,26 @@ int sim_pairing(int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64
     });
     return bad.load() ? -1 : 0;
 }
+// group-level ops of ops.cuh: gop 0/1 = G1/G2 validity, 2/3 = G1/G2 scalar multiplication
+int sim_group_op(int gop, const uint64_t *pts, const uint8_t *inf, const uint64_t *scalars, uint64_t *out, uint8_t *flag, size_t n) {
+    std::atomic<int> anybad{0};
+    const int w = (gop & 1) ? 24 : 12;
+    run_pair([&]() {
+        for (size_t i = 0; i < n; i++) {
+            bool bad = false;
+            uint8_t is_inf = inf ? inf[i] : 0, f = 0;
+            switch (gop) {
+                case GOP_G1_CHECK: f = g1_check_one(pts + w * i, is_inf, bad); break;
+                case GOP_G2_CHECK: f = g2_check_one(pts + w * i, is_inf, bad); break;
+                case GOP_G1_MUL: g1_mul_one(pts + w * i, is_inf, scalars + 4 * i, out + w * i, flag + i, bad); break;
+                default: g2_mul_one(pts + w * i, is_inf, scalars + 4 * i, out + w * i, flag + i, bad); break;
+            }
+            if (lane_or(bad)) anybad.store(1);
+            if (gop <= GOP_G2_CHECK && lane_par() == 0) flag[i] = f;
+        }
+    });
+    return anybad.load() ? -1 : 0;
+}
 // Montgomery-trick batch inversion of pairing.cuh (one simulated thread, runs of `run` elements)
 void sim_batch_inv(const uint64_t *in, uint64_t *out, size_t n, int run) {
     zkp_sim_par = 0;

@@ -248,6 +248,42 @@ def test_device_resident_path(engine, coracle):
     assert np.array_equal(a1.cpu().numpy().view(np.uint64), g1) and np.array_equal(a2.cpu().numpy().view(np.uint64), g2)
 
 
+def test_group_validity_checks(engine, coracle, pyref):
+    """SURVEY 8f-1: G1Affine::is_valid / G2Affine::is_valid (src/g1.rs:49-62, src/g2.rs:57-69) batched."""
+    g1, i1, e1, g2, i2, e2 = util.group_check_cases(pyref, coracle, n_valid=40)
+    assert list(engine.g1_check_batch(g1, i1)) == list(e1)
+    assert list(engine.g2_check_batch(g2, i2)) == list(e2)
+    # a larger batch of valid points, ragged size, no infinity array
+    a, _, b, _ = engine.gen_points(0x77, 0, 333)
+    assert not engine.g1_check_batch(a).any() and not engine.g2_check_batch(b).any()
+    b[17, 0] ^= np.uint64(1)
+    st = engine.g2_check_batch(b)
+    assert st[17] == 1 and st.sum() == 1
+    from zkvm_pairings_b200 import ZkpError
+    with pytest.raises(ZkpError):
+        bad = a.copy()
+        bad[3, :6] = util.fp_arr([pyref.P]).reshape(-1, 6)[0]
+        engine.g1_check_batch(bad)
+
+
+def test_group_scalar_mul_matches_oracle(engine, coracle):
+    """[k]P for 256-bit scalars (src/g1.rs:130-153 done correctly, src/g2.rs:185-208)."""
+    n = 77
+    k = util.random_scalars(n, seed=11)
+    b1, bi1, b2, bi2 = util.oracle_points(coracle, 0xC0FFEE, 5, n)
+    bi2[4] = 1
+    o1, f1 = engine.g1_mul_batch(b1, k, bi1)
+    o2, f2 = engine.g2_mul_batch(b2, k, bi2)
+    x1, xf1 = coracle.g1_mul_batch(k, b1, bi1)
+    x2, xf2 = coracle.g2_mul_batch(k, b2, bi2)
+    assert np.array_equal(f1, xf1) and np.array_equal(f2, xf2)
+    assert np.array_equal(o1[f1 == 0], x1[xf1 == 0]) and np.array_equal(o2[f2 == 0], x2[xf2 == 0])
+    # bilinearity through the engine's own scalar multiplication: e([a]P, Q) == e(P, [a]Q)
+    gt1 = engine.pairing_batch(o1[7:20], b2[7:20])
+    gt2 = engine.pairing_batch(b1[7:20], o2[7:20])
+    assert np.array_equal(gt1, gt2)
+
+
 def test_imad_peak_probe(engine):
     wide = engine.imad_peak(0)
     lo = engine.imad_peak(1)

@@ -195,6 +195,32 @@ def test_sim_point_generator_matches_oracle(sim, coracle):
     assert coracle.group_op("g2", "torsion_free", g2[0]) and coracle.group_op("g1", "torsion_free", g1[0])
 
 
+def test_sim_group_checks_and_scalar_mul(sim, coracle, pyref):
+    """G1/G2 is_valid semantics (src/g1.rs:49-62, src/g2.rs:57-69) and scalar
+    multiplication (src/g1.rs:130-153, src/g2.rs:185-208) of the device code vs the oracle."""
+    g1, i1, e1, g2, i2, e2 = util.group_check_cases(pyref, coracle)
+    st1, st2 = np.full(len(e1), 9, np.uint8), np.full(len(e2), 9, np.uint8)
+    assert sim.sim_group_op(0, _p(g1), _p(i1), None, None, _p(st1), ctypes.c_size_t(len(e1))) == 0
+    assert sim.sim_group_op(1, _p(g2), _p(i2), None, None, _p(st2), ctypes.c_size_t(len(e2))) == 0
+    assert list(st1) == list(e1) and list(st2) == list(e2)
+    for j in range(len(e1)):      # the C oracle agrees with the expectation the Python oracle produced
+        if not i1[j]:
+            assert coracle.group_op("g1", "on_curve", g1[j]) == (e1[j] != 1)
+    n = 9
+    k = util.random_scalars(n, seed=5)
+    b1, bi1, b2, bi2 = util.oracle_points(coracle, 0xBEEF, 3, n)
+    bi1[2] = 1                                      # identity base stays the identity
+    o1, f1 = np.zeros((n, 12), np.uint64), np.zeros(n, np.uint8)
+    o2, f2 = np.zeros((n, 24), np.uint64), np.zeros(n, np.uint8)
+    assert sim.sim_group_op(2, _p(b1), _p(bi1), _p(k), _p(o1), _p(f1), ctypes.c_size_t(n)) == 0
+    assert sim.sim_group_op(3, _p(b2), _p(bi2), _p(k), _p(o2), _p(f2), ctypes.c_size_t(n)) == 0
+    x1, xf1 = coracle.g1_mul_batch(k, b1, bi1)
+    x2, xf2 = coracle.g2_mul_batch(k, b2, bi2)
+    assert np.array_equal(f1, xf1) and np.array_equal(f2, xf2)
+    assert np.array_equal(o1[f1 == 0], x1[xf1 == 0]) and np.array_equal(o2[f2 == 0], x2[xf2 == 0])
+    assert f1[0] == 1 and f1[2] == 1 and f1[5] == 1 and f2[5] == 1     # k = 0, identity base, k = r
+
+
 def test_sim_batch_inversion(sim, coracle, pyref):
     """fp_batch_inv (Montgomery's trick, used between the two final-exponentiation launches): equal to
     element-wise Fermat inversion, zeros stay zero and do not poison their run, ragged last run."""
@@ -225,6 +251,9 @@ def test_sim_executed_mac_count(sim, coracle):
     sim.sim_pairing(3, _p(g1), None, _p(g2), None, ctypes.c_size_t(1), 4, None, _p(out), None)
     check4 = sim.sim_take_mac_count()
     assert (miller, fexp, check4) == (2052576, 2714568, 8942856)
+    a, o, st = util.random_fp_matrix(1, 1, seed=3), np.zeros((1, 6), np.uint64), np.zeros(1, np.uint8)
+    sim.sim_tower_op(5, _p(a), None, _p(o), _p(st), ctypes.c_size_t(1))
+    assert sim.sim_take_mac_count() == 364800        # the Fermat ladder both lanes would run: 2 x 608 x 300
     sys_path = os.path.join(ROOT, "bench.py")
     assert "4_767_144" in open(sys_path).read() and miller + fexp == 4767144
 

@@ -106,3 +106,57 @@ def oracle_points(coracle, seed, first, n):
     g1, i1 = coracle.g1_mul_batch(scalar_matrix(a))
     g2, i2 = coracle.g2_mul_batch(scalar_matrix(b))
     return g1, i1, g2, i2
+
+
+def group_check_cases(pyref, coracle, n_valid=4, seed=0x6F):
+    """Points for the validity checks with the status the reference semantics give them
+    (0 ok, 1 not on curve, 2 on the curve but outside the prime-order subgroup): valid multiples of
+    the generators, the identity, random off-curve pairs (what the reference's random() produces,
+    src/g1.rs:64-72), random curve points (cofactor != 1, so outside the subgroup) and the
+    reference's own G2 torsion KAT point (src/g2.rs:401-443)."""
+    import random
+    rng = random.Random(seed)
+    P = pyref.P
+    g1v, _, g2v, _ = oracle_points(coracle, seed, 0, n_valid)
+    g1, i1, e1 = [r for r in g1v], [0] * n_valid, [0] * n_valid
+    g2, i2, e2 = [r for r in g2v], [0] * n_valid, [0] * n_valid
+    g1.append(g1_to_arr((0, 1))); i1.append(1); e1.append(0)
+    g2.append(g2_to_arr(((0, 0), (1, 0)))); i2.append(1); e2.append(0)
+    for _ in range(3):
+        g1.append(g1_to_arr((rng.randrange(P), rng.randrange(P)))); i1.append(0); e1.append(1)
+        g2.append(g2_to_arr(((rng.randrange(P), rng.randrange(P)), (rng.randrange(P), rng.randrange(P))))); i2.append(0); e2.append(1)
+    cnt = 0
+    while cnt < 3:
+        x = rng.randrange(P)
+        y = pyref.fp_sqrt(pyref.fp_add(pyref.fp_mul(pyref.fp_square(x), x), pyref.B1))
+        if y is None:
+            continue
+        assert pyref.g1_is_on_curve((x, y, False)) and not pyref.g1_is_torsion_free((x, y, False))
+        g1.append(g1_to_arr((x, y))); i1.append(0); e1.append(2); cnt += 1
+    cnt = 0
+    while cnt < 3:
+        x = (rng.randrange(P), rng.randrange(P))
+        y = pyref.fp2_sqrt(pyref.fp2_add(pyref.fp2_mul(pyref.fp2_square(x), x), pyref.B2))
+        if y is None:
+            continue
+        assert pyref.g2_is_on_curve((x, y, False)) and not pyref.g2_is_torsion_free((x, y, False))
+        g2.append(g2_to_arr((x, y))); i2.append(0); e2.append(2); cnt += 1
+    # the reference's torsion KAT (src/g2.rs:401-443) holds zkcrypto's MONTGOMERY limbs, which in this
+    # crate's canonical storage are not a curve point at all: is_valid fails at the on-curve test
+    kat = golden("reference_kats.json")["g2_not_torsion_free"]["p"]     # x.c0, x.c1, y.c0, y.c1 as u64 limbs
+    kpt = [sum(int(h, 16) << (64 * i) for i, h in enumerate(limbs)) for limbs in kat]
+    assert not pyref.g2_is_on_curve(((kpt[0], kpt[1]), (kpt[2], kpt[3]), False))
+    assert not pyref.g2_is_torsion_free(((kpt[0], kpt[1]), (kpt[2], kpt[3]), False))
+    g2.append(np.array([int(h, 16) for limbs in kat for h in limbs], dtype=np.uint64)); i2.append(0); e2.append(1)
+    return (np.stack(g1), np.array(i1, np.uint8), np.array(e1, np.uint8),
+            np.stack(g2), np.array(i2, np.uint8), np.array(e2, np.uint8))
+
+
+def random_scalars(n, seed, edges=True):
+    """(n,4) little-endian u64 limbs of 256-bit scalars (edge cases first: 0, 1, 2, r-1, r, 2^256-1)."""
+    import random
+    rng = random.Random(seed)
+    R_ORDER = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    vals = [0, 1, 2, 3, R_ORDER - 1, R_ORDER, (1 << 256) - 1] if edges else []
+    vals = vals[:n] + [rng.getrandbits(256) for _ in range(max(0, n - len(vals)))]
+    return np.array([[(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)] for v in vals[:n]], dtype=np.uint64)

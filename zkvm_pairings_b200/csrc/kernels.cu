@@ -84,6 +84,29 @@ k_gen_points(uint64_t seed, uint64_t first, size_t n, uint64_t *__restrict__ g1,
     gen_g2_one(b, g2 + 24 * i, g2inf + i);
 }
 
+// Group-level batch ops: subgroup/on-curve validation and scalar multiplication.
+// gop = GroupOp; points are 12 (G1) or 24 (G2) u64 each; flag = status (checks) or is_infinity (mul).
+__global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS)
+k_group_op(int gop, const uint64_t *__restrict__ pts, const uint8_t *__restrict__ inf, const uint64_t *__restrict__ scalars,
+           uint64_t *__restrict__ out_pts, uint8_t *__restrict__ flag, uint32_t *err, size_t n) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    if (i >= n) return;
+    const int w = (gop & 1) ? 24 : 12;
+    bool bad = false;
+    uint8_t is_inf = inf ? inf[i] : 0, f = 0;
+    switch (gop) {
+        case GOP_G1_CHECK: f = g1_check_one(pts + (size_t)w * i, is_inf, bad); break;
+        case GOP_G2_CHECK: f = g2_check_one(pts + (size_t)w * i, is_inf, bad); break;
+        case GOP_G1_MUL: g1_mul_one(pts + (size_t)w * i, is_inf, scalars + 4 * i, out_pts + (size_t)w * i, flag + i, bad); break;
+        default: g2_mul_one(pts + (size_t)w * i, is_inf, scalars + 4 * i, out_pts + (size_t)w * i, flag + i, bad); break;
+    }
+    bad = lane_or(bad);
+    if (lane_par() == 0) {
+        if (gop <= GOP_G2_CHECK) flag[i] = f;
+        if (bad && err) atomicOr(err, 1u);
+    }
+}
+
 // Integer-multiply roofline probe.  Every chain gets its own multiplier and the multiplicand changes
 // every iteration, so nothing is loop invariant (ptxas would otherwise hoist the product and leave
 // 64-bit adds).  KIND 0: 8 independent IMAD.WIDE.U32 accumulate chains per thread; KIND 1: 8
@@ -442,7 +465,8 @@ static void slice_of(size_t n, size_t ndev, size_t d, size_t &lo, size_t &hi) {
 }
 
 struct HostJob {
-    int mode = 0;   // 1 miller, 2 final exp, 3 pairing ; 16 = tower op ; 32 = gen points
+    int mode = 0;   // 1 miller, 2 final exp, 3 pairing ; 16 = tower op ; 32 = gen points ; 48 = group op
+    const uint64_t *pts = nullptr, *scalars = nullptr;   // group op inputs (inf in g1inf, outputs in out / flags)
     const uint64_t *g1 = nullptr, *g2 = nullptr, *in12 = nullptr, *a = nullptr, *b = nullptr;
     const uint8_t *g1inf = nullptr, *g2inf = nullptr;
     uint64_t *out = nullptr, *og1 = nullptr, *og2 = nullptr;
@@ -488,6 +512,29 @@ static int32_t run_slice(zkp_ctx *ctx, DevState &d, const HostJob &j, size_t lo,
             CUS(cudaGetLastError());
             CUS(cudaMemcpyAsync(j.out + c0 * nr * 6, B[B_OUT].p, cn * nr * 48, cudaMemcpyDeviceToHost, st));
             if (j.flags) CUS(cudaMemcpyAsync(j.flags + c0, B[B_FLAG].p, cn, cudaMemcpyDeviceToHost, st));
+        } else if (j.mode == 48) {
+            const size_t w = (j.op & 1) ? 24 : 12;
+            const bool is_mul = j.op >= GOP_G1_MUL;
+            CUS(B[B_IN].ensure(cn * w * 8));
+            CUS(B[B_FLAG].ensure(cn));
+            CUS(cudaMemcpyAsync(B[B_IN].p, j.pts + c0 * w, cn * w * 8, cudaMemcpyHostToDevice, st));
+            const uint8_t *dinf = nullptr;
+            if (j.g1inf) {
+                CUS(B[B_G1INF].ensure(cn));
+                CUS(cudaMemcpyAsync(B[B_G1INF].p, j.g1inf + c0, cn, cudaMemcpyHostToDevice, st));
+                dinf = (const uint8_t *)B[B_G1INF].p;
+            }
+            if (is_mul) {
+                CUS(B[B_G2].ensure(cn * 32));
+                CUS(B[B_OUT].ensure(cn * w * 8));
+                CUS(cudaMemcpyAsync(B[B_G2].p, j.scalars + c0 * 4, cn * 32, cudaMemcpyHostToDevice, st));
+            }
+            k_group_op<<<grid_for(cn), ZKP_TPB, 0, st>>>(j.op, (const uint64_t *)B[B_IN].p, dinf, is_mul ? (const uint64_t *)B[B_G2].p : nullptr,
+                                                        is_mul ? (uint64_t *)B[B_OUT].p : nullptr, (uint8_t *)B[B_FLAG].p, d.d_err, cn);
+            ctx->launches++;
+            CUS(cudaGetLastError());
+            if (is_mul) CUS(cudaMemcpyAsync(j.out + c0 * w, B[B_OUT].p, cn * w * 8, cudaMemcpyDeviceToHost, st));
+            CUS(cudaMemcpyAsync(j.flags + c0, B[B_FLAG].p, cn, cudaMemcpyDeviceToHost, st));
         } else if (j.mode == 32) {
             CUS(B[B_G1].ensure(cn * 96));
             CUS(B[B_G2].ensure(cn * 192));
@@ -622,6 +669,28 @@ int32_t zkp_gen_points(zkp_ctx *ctx, uint64_t seed, uint64_t first, size_t n, ui
     HostJob j;
     j.mode = 32; j.seed = seed; j.first = first; j.og1 = g1; j.og1inf = g1inf; j.og2 = g2; j.og2inf = g2inf;
     return run_host_job(ctx, j, n);
+}
+
+static int32_t group_job(zkp_ctx *ctx, int gop, const uint64_t *pts, const uint8_t *inf, const uint64_t *scalars, size_t n,
+                         uint64_t *out, uint8_t *flags) {
+    if (n && (!pts || !flags || (gop >= GOP_G1_MUL && (!scalars || !out)))) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
+    HostJob j;
+    j.mode = 48; j.op = gop; j.pts = pts; j.g1inf = inf; j.scalars = scalars; j.out = out; j.flags = flags;
+    return run_host_job(ctx, j, n);
+}
+int32_t zkp_g1_check_batch(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_inf, size_t n, uint8_t *status) {
+    return group_job(ctx, GOP_G1_CHECK, g1_xy, g1_inf, nullptr, n, nullptr, status);
+}
+int32_t zkp_g2_check_batch(zkp_ctx *ctx, const uint64_t *g2_xy, const uint8_t *g2_inf, size_t n, uint8_t *status) {
+    return group_job(ctx, GOP_G2_CHECK, g2_xy, g2_inf, nullptr, n, nullptr, status);
+}
+int32_t zkp_g1_mul_batch(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_inf, const uint64_t *scalars, size_t n,
+                         uint64_t *out_xy, uint8_t *out_inf) {
+    return group_job(ctx, GOP_G1_MUL, g1_xy, g1_inf, scalars, n, out_xy, out_inf);
+}
+int32_t zkp_g2_mul_batch(zkp_ctx *ctx, const uint64_t *g2_xy, const uint8_t *g2_inf, const uint64_t *scalars, size_t n,
+                         uint64_t *out_xy, uint8_t *out_inf) {
+    return group_job(ctx, GOP_G2_MUL, g2_xy, g2_inf, scalars, n, out_xy, out_inf);
 }
 
 // One large product: per-device Miller loops over a contiguous slice -> per-device Fp12 partial ->

@@ -230,4 +230,64 @@ ZKP_HD void gen_g2_one(uint64_t k, uint64_t *xy, uint8_t *inf) {
     store_fp2(xy + 12, ay, nullptr);
 }
 
+// ------------------------------------------------------------------ group-level batch ops
+
+enum GroupOp { GOP_G1_CHECK = 0, GOP_G2_CHECK = 1, GOP_G1_MUL = 2, GOP_G2_MUL = 3 };
+#ifndef ZKP_POINT_OK   /* same values as include/zkpair.h */
+#define ZKP_POINT_OK 0
+#define ZKP_POINT_NOT_ON_CURVE 1
+#define ZKP_POINT_NOT_TORSION_FREE 2
+#endif
+
+// |x|^2 (128 bits): G1 subgroup test -[x^2]P == (beta x, y), src/g1.rs:103-115
+ZKP_HD uint8_t g1_check_one(const uint64_t *xy, uint8_t inf, bool &bad) {
+    Fp x = load_fp(xy, bad), y = load_fp(xy + 6, bad);
+    if (inf) return ZKP_POINT_OK;                                             // src/g1.rs:50-52
+    Fp rhs = fp_add(fmul(fsqr(x), x), fp_const(ZKP_B1));                      // y^2 = x^3 + 4, src/g1.rs:95-101
+    if (!fp_is_zero(fp_sub(fsqr(y), rhs))) return ZKP_POINT_NOT_ON_CURVE;
+    const uint64_t xx[2] = {(uint64_t)(ZKP_BLS_X * ZKP_BLS_X), (uint64_t)(((unsigned __int128)ZKP_BLS_X * ZKP_BLS_X) >> 64)};
+    Jac<OpsFp> acc;
+    scalar_mul_jac<OpsFp>(acc, x, y, xx, 128);
+    // -[x^2]P == (beta x, y)  <=>  [x^2]P == -(beta x, y)
+    return jac_equals_neg_affine<OpsFp>(acc, fmul(x, fp_const(ZKP_BETA)), y) ? ZKP_POINT_OK : ZKP_POINT_NOT_TORSION_FREE;
+}
+// G2 subgroup test psi(Q) == -[|x|]Q, src/g2.rs:126-170
+ZKP_HD uint8_t g2_check_one(const uint64_t *xy, uint8_t inf, bool &bad) {
+    Fp2 x = load_fp2(xy, bad), y = load_fp2(xy + 12, bad);
+    if (inf) return ZKP_POINT_OK;                                             // src/g2.rs:58-60
+    Fp2 b2;
+    b2.c = fp_const(ZKP_B1);                                                  // b' = 4 + 4u, src/common.rs:70-71
+    Fp2 rhs = fp2_add(fp2_mul(fp2_sqr(x), x), b2);
+    if (!fp2_is_zero(fp2_sub(fp2_sqr(y), rhs))) return ZKP_POINT_NOT_ON_CURVE;
+    const uint64_t k[1] = {ZKP_BLS_X};
+    Jac<OpsFp2> acc;
+    scalar_mul_jac<OpsFp2>(acc, x, y, k, 64);
+    Fp2 px = fp2_mul(fp2_conj(x), fp2_const(ZKP_PSI));
+    Fp2 py = fp2_mul(fp2_conj(y), fp2_const(ZKP_PSI + 2 * ZKP_NL));
+    return jac_equals_neg_affine<OpsFp2>(acc, px, py) ? ZKP_POINT_OK : ZKP_POINT_NOT_TORSION_FREE;
+}
+// [k]P for a 256-bit scalar k (4 little-endian u64, the limbs of an Fr, src/fr.rs).  Correct
+// double-and-add over all 256 bits (the reference's G1 `Mul<&Fr>` drops bit 0, src/g1.rs:138-142).
+ZKP_HD void g1_mul_one(const uint64_t *xy, uint8_t inf, const uint64_t *k, uint64_t *out_xy, uint8_t *out_inf, bool &bad) {
+    Fp x = load_fp(xy, bad), y = load_fp(xy + 6, bad), ax, ay;
+    bool is_inf = true;
+    if (inf) { ax = fp_zero(); ay = fp_one(); }
+    else is_inf = scalar_mul_affine<OpsFp>(ax, ay, x, y, k, 256);
+    if (lane_par() == 0) {
+        *out_inf = is_inf ? 1 : 0;
+        store_fp(out_xy, ax, nullptr);
+    } else {
+        store_fp(out_xy + 6, ay, nullptr);
+    }
+}
+ZKP_HD void g2_mul_one(const uint64_t *xy, uint8_t inf, const uint64_t *k, uint64_t *out_xy, uint8_t *out_inf, bool &bad) {
+    Fp2 x = load_fp2(xy, bad), y = load_fp2(xy + 12, bad), ax, ay;
+    bool is_inf = true;
+    if (inf) { ax = fp2_zero(); ay = fp2_one(); }
+    else is_inf = scalar_mul_affine<OpsFp2>(ax, ay, x, y, k, 256);
+    if (lane_par() == 0) *out_inf = is_inf ? 1 : 0;
+    store_fp2(out_xy, ax, nullptr);
+    store_fp2(out_xy + 12, ay, nullptr);
+}
+
 }  // namespace zkp

@@ -266,24 +266,39 @@ ZKP_NOINLINE void jac_add_affine(Jac<O> &r, const Jac<O> &p, const typename O::T
     r.z = O::sub(O::sub(O::sqr(O::add(p.z, h)), z1z1), hh);
     r.x = x3;
 }
-// [k]Q, MSB-first double-and-add over `nbits` scalar bits; returns affine (ax, ay), inf flag
+// [k]Q in Jacobian coordinates, MSB-first double-and-add over `nbits` scalar bits
 template <class O>
-ZKP_HD bool scalar_mul_affine(typename O::T &ax, typename O::T &ay, const typename O::T &qx, const typename O::T &qy,
-                              const uint64_t *k, int nbits) {
-    typedef typename O::T T;
-    Jac<O> acc;
+ZKP_HD void scalar_mul_jac(Jac<O> &acc, const typename O::T &qx, const typename O::T &qy, const uint64_t *k, int nbits) {
     acc.x = O::zero(); acc.y = O::one(); acc.z = O::zero();
 #pragma unroll 1
     for (int i = nbits - 1; i >= 0; i--) {
         jac_double(acc, acc);
         if ((k[i >> 6] >> (i & 63)) & 1) jac_add_affine(acc, acc, qx, qy);
     }
+}
+// [k]Q as an affine point (ax, ay); returns the infinity flag
+template <class O>
+ZKP_HD bool scalar_mul_affine(typename O::T &ax, typename O::T &ay, const typename O::T &qx, const typename O::T &qy,
+                              const uint64_t *k, int nbits) {
+    typedef typename O::T T;
+    Jac<O> acc;
+    scalar_mul_jac<O>(acc, qx, qy, k, nbits);
     if (O::is_zero(acc.z)) { ax = O::zero(); ay = O::one(); return true; }   // identity = (0,1,inf) src/g1.rs:25-31
     T zi = O::inv(acc.z);
     T zi2 = O::sqr(zi);
     ax = O::mul(acc.x, zi2);
     ay = O::mul(acc.y, O::mul(zi2, zi));
     return false;
+}
+// Jacobian p == -(affine (x, y)) without an inversion: X == x Z^2 and Y == -y Z^3 (false at infinity)
+template <class O>
+ZKP_HD bool jac_equals_neg_affine(const Jac<O> &p, const typename O::T &x, const typename O::T &y) {
+    typedef typename O::T T;
+    if (O::is_zero(p.z)) return false;
+    T zz = O::sqr(p.z);
+    bool ex = O::is_zero(O::sub(p.x, O::mul(x, zz)));
+    bool ey = O::is_zero(O::add(p.y, O::mul(y, O::mul(zz, p.z))));
+    return ex & ey;
 }
 
 }  // namespace zkp

@@ -222,6 +222,46 @@ class PairingEngine:
         self._check(self._lib.zkp_gen_points(self._ctx, seed, first, n, _ptr(g1), _ptr(i1), _ptr(g2), _ptr(i2)))
         return g1, i1, g2, i2
 
+    # ------------------------------------------------------------------ group-level ops
+    def _pts(self, pts, width, inf):
+        pts = np.ascontiguousarray(pts, dtype=np.uint64).reshape(-1, width)
+        n = pts.shape[0]
+        if inf is not None:
+            inf = np.ascontiguousarray(inf, dtype=np.uint8).reshape(-1)
+            if inf.shape[0] != n:
+                raise ValueError("infinity flags do not match the number of points")
+        return pts, inf, n
+
+    def g1_check_batch(self, g1, g1_inf=None):
+        """G1Affine::is_valid per point (src/g1.rs:49-62) -> uint8 status: 0 ok, 1 not on curve, 2 not torsion free."""
+        pts, inf, n = self._pts(g1, 12, g1_inf)
+        st = np.zeros(n, np.uint8)
+        self._check(self._lib.zkp_g1_check_batch(self._ctx, _ptr(pts), _ptr(inf), n, _ptr(st)))
+        return st
+
+    def g2_check_batch(self, g2, g2_inf=None):
+        """G2Affine::is_valid per point (src/g2.rs:57-69) -> uint8 status."""
+        pts, inf, n = self._pts(g2, 24, g2_inf)
+        st = np.zeros(n, np.uint8)
+        self._check(self._lib.zkp_g2_check_batch(self._ctx, _ptr(pts), _ptr(inf), n, _ptr(st)))
+        return st
+
+    def _mul(self, fn, pts, width, inf, scalars):
+        pts, inf, n = self._pts(pts, width, inf)
+        k = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+        if k.shape[0] != n:
+            raise ValueError("one 4-limb scalar per point expected")
+        out, oinf = np.empty((n, width), np.uint64), np.zeros(n, np.uint8)
+        self._check(fn(self._ctx, _ptr(pts), _ptr(inf), _ptr(k), n, _ptr(out), _ptr(oinf)))
+        return out, oinf
+
+    def g1_mul_batch(self, g1, scalars, g1_inf=None):
+        """[k_i]P_i (scalars: (n,4) little-endian u64 limbs of an Fr) -> (points (n,12), is_infinity (n,))."""
+        return self._mul(self._lib.zkp_g1_mul_batch, g1, 12, g1_inf, scalars)
+
+    def g2_mul_batch(self, g2, scalars, g2_inf=None):
+        return self._mul(self._lib.zkp_g2_mul_batch, g2, 24, g2_inf, scalars)
+
     # ------------------------------------------------------------------ device-resident (torch tensors)
     def pairing_dev(self, mode: int, out, g1=None, g2=None, g1_inf=None, g2_inf=None, in_fp12=None, n_checks=None,
                     pairs_per_check: int = 1, is_one=None, err=None, stream: int = 0, dev: int = 0):
