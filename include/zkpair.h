@@ -171,6 +171,17 @@ int32_t zkp_gen_points_dev(zkp_ctx *ctx, int32_t dev, uint64_t seed, uint64_t fi
 int32_t zkp_gen_points(zkp_ctx *ctx, uint64_t seed, uint64_t first, size_t n, uint64_t *g1_xy,
                        uint8_t *g1_inf, uint64_t *g2_xy, uint8_t *g2_inf);
 
+/* ---- byte (de)serialisation ----------------------------------------------------------
+ * Fp::from_bytes (src/fp.rs:165-191): n x 48 big-endian bytes -> n x 6 little-endian u64 limbs;
+ * ok[i] = 1 when the value is canonical (< p, the reference's Ok), 0 for the reference's Err(())
+ * (the limbs are still written).  Fp::to_bytes (src/fp.rs:195-207) is the inverse, no check.  An Fp2 /
+ * Fp6 / Fp12 / point is a run of Fp, so the same calls serialise them coefficient by coefficient. */
+int32_t zkp_fp_from_bytes_batch(zkp_ctx *ctx, const uint8_t *bytes, size_t n, uint64_t *out_limbs, uint8_t *ok);
+int32_t zkp_fp_to_bytes_batch(zkp_ctx *ctx, const uint64_t *limbs, size_t n, uint8_t *out_bytes);
+/* device-resident form: dir 0 = from_bytes, 1 = to_bytes; buffers 16-byte aligned; d_ok may be NULL */
+int32_t zkp_fp_bytes_dev(zkp_ctx *ctx, int32_t dev, int32_t dir, const void *d_in, void *d_out, uint8_t *d_ok,
+                         size_t n, void *stream);
+
 /* ---- group-level batch operations (the callers either side of a pairing) ------------ */
 
 /* status byte per point */

@@ -248,6 +248,24 @@ def test_device_resident_path(engine, coracle):
     assert np.array_equal(a1.cpu().numpy().view(np.uint64), g1) and np.array_equal(a2.cpu().numpy().view(np.uint64), g2)
 
 
+def test_fp_byte_serialisation(engine, pyref):
+    """SURVEY 8f-2: Fp::from_bytes / to_bytes (src/fp.rs:165-207): big-endian, canonical check, round trip."""
+    P = pyref.P
+    vals = [0, 1, P - 1, P, P + 1, (1 << 384) - 1, 0x0102030405060708090a0b0c0d0e0f101112131415161718191a1b1c1d1e1f202122232425262728292a2b2c2d2e2f30]
+    rng = np.random.default_rng(5)
+    data = np.concatenate([np.frombuffer(b"".join(v.to_bytes(48, "big") for v in vals), np.uint8).reshape(-1, 48),
+                           rng.integers(0, 256, size=(1000, 48), dtype=np.uint8)])
+    limbs, ok = engine.fp_from_bytes_batch(data)
+    for row, lim, k in zip(data, limbs, ok):
+        v = int.from_bytes(row.tobytes(), "big")
+        assert sum(int(x) << (64 * i) for i, x in enumerate(lim)) == v
+        assert bool(k) == (pyref.fp_from_bytes(row.tobytes()) is not None) == (v < P)
+    back = engine.fp_to_bytes_batch(limbs)
+    assert np.array_equal(back, data)
+    assert engine.fp_to_bytes_batch(util.fp_arr([5]).reshape(-1, 6)).tobytes() == pyref.fp_to_bytes(5)
+    assert engine.fp_from_bytes_batch(np.zeros((0, 48), np.uint8))[0].shape == (0, 6)
+
+
 def test_group_validity_checks(engine, coracle, pyref):
     """SURVEY 8f-1: G1Affine::is_valid / G2Affine::is_valid (src/g1.rs:49-62, src/g2.rs:57-69) batched."""
     g1, i1, e1, g2, i2, e2 = util.group_check_cases(pyref, coracle, n_valid=40)

@@ -107,6 +107,40 @@ k_group_op(int gop, const uint64_t *__restrict__ pts, const uint8_t *__restrict_
     }
 }
 
+// Byte (de)serialisation at the boundary: 48 big-endian bytes <-> six little-endian u64
+// limbs, Fp::from_bytes / Fp::to_bytes (src/fp.rs:165-207).  Pure byte shuffling, HBM bound: one
+// thread moves one element with three 128-bit loads and three 128-bit stores (a warp covers 1536
+// contiguous bytes on both sides).  dir 0: bytes -> limbs (+ canonical flag), dir 1: limbs -> bytes.
+__device__ __forceinline__ uint64_t bswap64(uint64_t x) {
+    uint32_t lo = __byte_perm((uint32_t)x, 0, 0x0123), hi = __byte_perm((uint32_t)(x >> 32), 0, 0x0123);
+    return ((uint64_t)lo << 32) | hi;
+}
+__global__ void __launch_bounds__(256) k_fp_bytes(int dir, const uint4 *__restrict__ in, uint4 *__restrict__ out,
+                                                  uint8_t *__restrict__ ok, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 a = in[3 * i], b = in[3 * i + 1], c = in[3 * i + 2];
+    // reversing all 48 bytes: the three 16-byte chunks swap ends, each chunk is byte-reversed
+    uint64_t w[6] = {((uint64_t)a.y << 32) | a.x, ((uint64_t)a.w << 32) | a.z, ((uint64_t)b.y << 32) | b.x,
+                     ((uint64_t)b.w << 32) | b.z, ((uint64_t)c.y << 32) | c.x, ((uint64_t)c.w << 32) | c.z};
+    uint64_t r[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) r[k] = bswap64(w[5 - k]);
+    out[3 * i] = make_uint4((uint32_t)r[0], (uint32_t)(r[0] >> 32), (uint32_t)r[1], (uint32_t)(r[1] >> 32));
+    out[3 * i + 1] = make_uint4((uint32_t)r[2], (uint32_t)(r[2] >> 32), (uint32_t)r[3], (uint32_t)(r[3] >> 32));
+    out[3 * i + 2] = make_uint4((uint32_t)r[4], (uint32_t)(r[4] >> 32), (uint32_t)r[5], (uint32_t)(r[5] >> 32));
+    if (dir == 0 && ok) {   // canonical: value < p (src/fp.rs:176-190)
+        uint64_t borrow = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            uint64_t pk = ((uint64_t)ZKP_P[2 * k + 1] << 32) | ZKP_P[2 * k];
+            uint64_t d = r[k] - pk;
+            borrow = (r[k] < pk) | (d < borrow);
+        }
+        ok[i] = (uint8_t)borrow;   // 1 = canonical (Ok), 0 = Err(())
+    }
+}
+
 // Integer-multiply roofline probe.  Every chain gets its own multiplier and the multiplicand changes
 // every iteration, so nothing is loop invariant (ptxas would otherwise hoist the product and leave
 // 64-bit adds).  KIND 0: 8 independent IMAD.WIDE.U32 accumulate chains per thread; KIND 1: 8
@@ -669,6 +703,56 @@ int32_t zkp_gen_points(zkp_ctx *ctx, uint64_t seed, uint64_t first, size_t n, ui
     HostJob j;
     j.mode = 32; j.seed = seed; j.first = first; j.og1 = g1; j.og1inf = g1inf; j.og2 = g2; j.og2inf = g2inf;
     return run_host_job(ctx, j, n);
+}
+
+// bytes <-> limbs on device-resident buffers (dir 0: from_bytes, 1: to_bytes)
+int32_t zkp_fp_bytes_dev(zkp_ctx *ctx, int32_t dev, int32_t dir, const void *d_in, void *d_out, uint8_t *d_ok, size_t n, void *stream) {
+    int32_t rc = check_dev(ctx, dev);
+    if (rc) return rc;
+    if (n && (!d_in || !d_out)) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
+    if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return fail(ZKP_ERR_INVALID_ARG, "buffers must be 16-byte aligned");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState &d = ctx->devs[dev];
+    CU(cudaSetDevice(d.id));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
+    if (n) {
+        k_fp_bytes<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dir, (const uint4 *)d_in, (uint4 *)d_out, d_ok, n);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    return ZKP_OK;
+}
+static int32_t bytes_job(zkp_ctx *ctx, int dir, const void *in, void *out, uint8_t *ok, size_t n) {
+    if (!ctx) return fail(ZKP_ERR_INVALID_ARG, "ctx is NULL");
+    if (n == 0) return ZKP_OK;
+    if (!in || !out) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState &d = ctx->devs[0];   // HBM-bound byte shuffling: one device is already PCIe-limited
+    CU(cudaSetDevice(d.id));
+    cudaStream_t st = d.stream[0];
+    DevBuf *B = d.buf[0];
+    const size_t chunk = (size_t)ZKP_CHUNK * 8;
+    for (size_t c0 = 0; c0 < n; c0 += chunk) {
+        size_t cn = n - c0 < chunk ? n - c0 : chunk;
+        CU(B[B_IN].ensure(cn * 48));
+        CU(B[B_OUT].ensure(cn * 48));
+        CU(B[B_FLAG].ensure(cn));
+        CU(cudaMemcpyAsync(B[B_IN].p, (const uint8_t *)in + c0 * 48, cn * 48, cudaMemcpyHostToDevice, st));
+        k_fp_bytes<<<(unsigned)((cn + 255) / 256), 256, 0, st>>>(dir, (const uint4 *)B[B_IN].p, (uint4 *)B[B_OUT].p,
+                                                                  ok ? (uint8_t *)B[B_FLAG].p : nullptr, cn);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync((uint8_t *)out + c0 * 48, B[B_OUT].p, cn * 48, cudaMemcpyDeviceToHost, st));
+        if (ok && dir == 0) CU(cudaMemcpyAsync(ok + c0, B[B_FLAG].p, cn, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return ZKP_OK;
+}
+int32_t zkp_fp_from_bytes_batch(zkp_ctx *ctx, const uint8_t *bytes, size_t n, uint64_t *out_limbs, uint8_t *ok) {
+    return bytes_job(ctx, 0, bytes, out_limbs, ok, n);
+}
+int32_t zkp_fp_to_bytes_batch(zkp_ctx *ctx, const uint64_t *limbs, size_t n, uint8_t *out_bytes) {
+    return bytes_job(ctx, 1, limbs, out_bytes, nullptr, n);
 }
 
 static int32_t group_job(zkp_ctx *ctx, int gop, const uint64_t *pts, const uint8_t *inf, const uint64_t *scalars, size_t n,

@@ -222,6 +222,25 @@ class PairingEngine:
         self._check(self._lib.zkp_gen_points(self._ctx, seed, first, n, _ptr(g1), _ptr(i1), _ptr(g2), _ptr(i2)))
         return g1, i1, g2, i2
 
+    # ------------------------------------------------------------------ byte (de)serialisation
+    def fp_from_bytes_batch(self, data):
+        """Fp::from_bytes (src/fp.rs:165-191): (n,48) big-endian bytes -> (limbs (n,6) uint64, ok (n,) uint8)."""
+        b = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1, 48)
+        n = b.shape[0]
+        out, ok = np.empty((n, 6), np.uint64), np.zeros(n, np.uint8)
+        self._check(self._lib.zkp_fp_from_bytes_batch(self._ctx, _ptr(b), n, _ptr(out), _ptr(ok)))
+        return out, ok
+
+    def fp_to_bytes_batch(self, limbs):
+        """Fp::to_bytes (src/fp.rs:195-207): (n,6) uint64 limbs -> (n,48) big-endian bytes."""
+        a = np.ascontiguousarray(limbs, dtype=np.uint64).reshape(-1, 6)
+        out = np.empty((a.shape[0], 48), np.uint8)
+        self._check(self._lib.zkp_fp_to_bytes_batch(self._ctx, _ptr(a), a.shape[0], _ptr(out)))
+        return out
+
+    def fp_bytes_dev(self, direction: int, d_in, d_out, n: int, ok=None, stream: int = 0, dev: int = 0):
+        self._check(self._lib.zkp_fp_bytes_dev(self._ctx, dev, direction, _dptr(d_in), _dptr(d_out), _dptr(ok), n, ctypes.c_void_p(stream)))
+
     # ------------------------------------------------------------------ group-level ops (SURVEY 8f)
     def _pts(self, pts, width, inf):
         pts = np.ascontiguousarray(pts, dtype=np.uint64).reshape(-1, width)
