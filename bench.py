@@ -294,7 +294,10 @@ def run_ours(args):
             # best wide-MAC rate measured in this run on this GPU (the pipe sustains one IMAD.WIDE per
             # 4 cycles per scheduler: 148 SM x 4 x 8 lanes x clock)
             "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T wide-MAC/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the step's three launches in the ncu --set
+                         # full capture of a 2^16 step (profiles/r1h_ncu_summary.txt: 4.50 GB), scaled to this batch
+                         "traffic": 4.50e9 * n / 65536.0,
                          "kernel": "k_pairing<1> + k_fe_batch_inv + k_fe_finish (one step)", "kernel_ms": per_launch_ms, "algorithmic_macs_per_pairing": MACS_PER_PAIRING,
                          "executed_macs_per_pairing": EXECUTED_MACS_PER_PAIRING,
                          "executed_frac": pairs_per_s_kernel * EXECUTED_MACS_PER_PAIRING / peak,

@@ -171,6 +171,30 @@ int32_t zkp_gen_points_dev(zkp_ctx *ctx, int32_t dev, uint64_t seed, uint64_t fi
 int32_t zkp_gen_points(zkp_ctx *ctx, uint64_t seed, uint64_t first, size_t n, uint64_t *g1_xy,
                        uint8_t *g1_inf, uint64_t *g2_xy, uint8_t *g2_inf);
 
+/* ---- prepared G2 points (`G2Prepared` of the zkcrypto lineage, absent from the reference) --
+ * The 68 line-coefficient triples the Miller loop derives from a G2 point (63 doubling + 5 addition
+ * steps), computed once for points that are fixed across checks -- the verifying-key points of a
+ * Groth16-style check -- so that those pairs skip the G2 arithmetic in every check.  A table is an
+ * opaque blob of ZKP_G2_PREPARED_U64 u64 per point in the library's internal (Montgomery) limb format,
+ * valid for this build of the library only; results are bit-identical to the unprepared calls. */
+#define ZKP_G2_PREPARED_U64 (68 * 3 * 12)
+int32_t zkp_g2_prepare_batch(zkp_ctx *ctx, const uint64_t *g2_xy, size_t n, uint64_t *out_tables);
+int32_t zkp_g2_prepare_dev(zkp_ctx *ctx, int32_t dev, const uint64_t *d_g2_xy, size_t n, uint64_t *d_out_tables,
+                           uint32_t *d_err, void *stream);
+/* n_checks products of k pairs with a shared final exponentiation, like zkp_multi_pairing_batch, where
+ * the LAST kf pairs of every check take their G2 point from `tables` (kf tables shared by all checks;
+ * tables_inf = their is_infinity flags or NULL) and only the first k - kf pairs have per-check G2
+ * points: g1_xy holds n_checks * k points, g2_xy holds n_checks * (k - kf). */
+int32_t zkp_multi_pairing_prepared_batch(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_inf,
+                                         const uint64_t *g2_xy, const uint8_t *g2_inf, size_t n_checks,
+                                         int32_t pairs_per_check, const uint64_t *tables, const uint8_t *tables_inf,
+                                         int32_t prepared_pairs, uint64_t *out_gt, uint8_t *out_is_one);
+int32_t zkp_multi_pairing_prepared_dev(zkp_ctx *ctx, int32_t dev, const uint64_t *d_g1_xy, const uint8_t *d_g1_inf,
+                                       const uint64_t *d_g2_xy, const uint8_t *d_g2_inf, size_t n_checks,
+                                       int32_t pairs_per_check, const uint64_t *d_tables, const uint8_t *d_tables_inf,
+                                       int32_t prepared_pairs, uint64_t *d_out_gt, uint8_t *d_is_one, uint32_t *d_err,
+                                       void *stream);
+
 /* ---- byte (de)serialisation ----------------------------------------------------------
  * Fp::from_bytes (src/fp.rs:165-191): n x 48 big-endian bytes -> n x 6 little-endian u64 limbs;
  * ok[i] = 1 when the value is canonical (< p, the reference's Ok), 0 for the reference's Err(())

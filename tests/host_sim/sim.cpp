@@ -91,6 +91,36 @@ int sim_pairing(int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64
     });
     return bad.load() ? -1 : 0;
 }
+// prepared G2 line tables: same blob layout as the GPU kernel k_g2_prepare
+void sim_g2_prepare(const uint64_t *g2, size_t n, uint64_t *out) {
+    run_pair([&]() {
+        for (size_t i = 0; i < n; i++) {
+            bool bad = false;
+            G2A q;
+            load_g2(q, g2 + 24 * i, bad);
+            g2_prepare(q, (Fp *)out + i * (ZKP_LINE_STEPS * 3 * 2) + lane_par());
+        }
+    });
+}
+// n checks of k pairs, the last kf of them from the tables `tab`; full pairing (mode 3)
+int sim_pairing_prepared(const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf, size_t n, int k,
+                         const uint64_t *tab, const uint8_t *tabinf, int kf, uint64_t *out, uint8_t *is_one) {
+    std::atomic<int> anybad{0};
+    run_pair([&]() {
+        for (size_t i = 0; i < n; i++) {
+            bool bad = false;
+            Fp12 f;
+            size_t e = i * (size_t)k, e2 = i * (size_t)(k - kf);
+            pairing_front<8>(f, bad, 3, g1 + 12 * e, g1inf ? g1inf + e : nullptr, g2 ? g2 + 24 * e2 : nullptr,
+                             g2inf ? g2inf + e2 : nullptr, k, nullptr, (const Fp *)tab, tabinf, kf);
+            final_exponentiation(f, f);
+            bool one = store_fp12(out + 72 * i, f);
+            if (is_one && lane_par() == 0) is_one[i] = one ? 1 : 0;
+            if (lane_or(bad)) anybad.store(1);
+        }
+    });
+    return anybad.load() ? -1 : 0;
+}
 // group-level ops of ops.cuh: gop 0/1 = G1/G2 validity, 2/3 = G1/G2 scalar multiplication
 int sim_group_op(int gop, const uint64_t *pts, const uint8_t *inf, const uint64_t *scalars, uint64_t *out, uint8_t *flag, size_t n) {
     std::atomic<int> anybad{0};

@@ -248,6 +248,28 @@ def test_device_resident_path(engine, coracle):
     assert np.array_equal(a1.cpu().numpy().view(np.uint64), g1) and np.array_equal(a2.cpu().numpy().view(np.uint64), g2)
 
 
+def test_prepared_g2_tables(engine, coracle):
+    """G2Prepared-style line tables: Groth16-shaped checks (4 pairs, 3 verifying-key G2 points
+    prepared once) equal the unprepared results and the oracle bit for bit, including corrupted checks."""
+    nc, k, kf = 257, 4, 3
+    g1, _, g2all, _ = engine.gen_points(0x6716, 0, nc * k)
+    fixed = g2all[:kf].copy()
+    g2 = g2all.reshape(nc, k, 24).copy()
+    g2[:, k - kf:, :] = fixed
+    tab = engine.g2_prepare_batch(fixed)
+    assert tab.shape == (kf, 68 * 3 * 12)
+    var = np.ascontiguousarray(g2[:, :k - kf, :]).reshape(-1, 24)
+    gt, one = engine.multi_pairing_prepared_batch(g1, var, k, tab)
+    ref, ref_one = engine.multi_pairing_batch(g1, g2.reshape(-1, 24), k)
+    assert np.array_equal(gt, ref) and np.array_equal(one, ref_one)
+    exp, _ = coracle.multi_pairing_batch(g1[:16 * k], None, g2.reshape(-1, 24)[:16 * k], None, k)
+    assert np.array_equal(gt[:16], exp)
+    # all pairs prepared (k = kf = 2), second table flagged infinite
+    gt2, _ = engine.multi_pairing_prepared_batch(g1[:10], None, 2, tab[:2], tables_inf=np.array([0, 1], np.uint8))
+    exp2, _ = coracle.multi_pairing_batch(g1[:10], None, np.tile(fixed[:2], (5, 1)), np.tile(np.array([0, 1], np.uint8), 5), 2)
+    assert np.array_equal(gt2, exp2)
+
+
 def test_fp_byte_serialisation(engine, pyref):
     """SURVEY 8f-2: Fp::from_bytes / to_bytes (src/fp.rs:165-207): big-endian, canonical check, round trip."""
     P = pyref.P

@@ -221,6 +221,29 @@ def test_sim_group_checks_and_scalar_mul(sim, coracle, pyref):
     assert f1[0] == 1 and f1[2] == 1 and f1[5] == 1 and f2[5] == 1     # k = 0, identity base, k = r
 
 
+def test_sim_prepared_g2_tables(sim, coracle):
+    """Miller loop over prepared line tables == the plain multi-pairing, bit for bit
+    (k = 4 with the last 3 pairs prepared, k = 2 all prepared, a prepared pair at infinity)."""
+    nc, k, kf = 3, 4, 3
+    g1, _, g2all, _ = util.oracle_points(coracle, 0xABCD, 0, nc * k)
+    fixed = g2all[:kf].copy()                                   # the shared "verifying-key" points
+    g2 = g2all.reshape(nc, k, 24).copy()
+    g2[:, k - kf:, :] = fixed                                   # every check ends with the same kf G2 points
+    tab = np.zeros((kf, 68 * 3 * 12), np.uint64)
+    sim.sim_g2_prepare(_p(fixed), ctypes.c_size_t(kf), _p(tab))
+    var = np.ascontiguousarray(g2[:, :k - kf, :]).reshape(-1, 24)
+    out, one = np.zeros((nc, 72), np.uint64), np.zeros(nc, np.uint8)
+    assert sim.sim_pairing_prepared(_p(g1), None, _p(var), None, ctypes.c_size_t(nc), k, _p(tab), None, kf, _p(out), _p(one)) == 0
+    exp, exp_one = coracle.multi_pairing_batch(g1, None, g2.reshape(-1, 24), None, k)
+    assert np.array_equal(out, exp) and np.array_equal(one, exp_one)
+    # all pairs prepared, one table flagged as the point at infinity
+    ti = np.array([0, 1], np.uint8)
+    out2 = np.zeros((1, 72), np.uint64)
+    assert sim.sim_pairing_prepared(_p(g1[:2]), None, None, None, ctypes.c_size_t(1), 2, _p(tab[:2]), _p(ti), 2, _p(out2), None) == 0
+    exp2, _ = coracle.multi_pairing_batch(g1[:2], None, fixed[:2], ti, 2)
+    assert np.array_equal(out2, exp2)
+
+
 def test_sim_batch_inversion(sim, coracle, pyref):
     """fp_batch_inv (Montgomery's trick, used between the two final-exponentiation launches): equal to
     element-wise Fermat inversion, zeros stay zero and do not poison their run, ragged last run."""

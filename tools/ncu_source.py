@@ -10,7 +10,7 @@ tot = collections.Counter(); byop = collections.Counter(); execop = collections.
 opstall = collections.defaultdict(collections.Counter)
 insts = []
 for r in rows[2:]:
-    if len(r) < len(hdr): continue
+    if len(r) < len(hdr) or not r[ix['# Samples']].strip().isdigit(): continue   # kernel/header rows of multi-kernel reports
     src = r[ix['Source']].strip()
     op = src.split()[0] if not src.startswith('@') else src.split()[1]
     op = op.rstrip(';')

@@ -51,4 +51,12 @@ ms = timed(lambda: eng.pairing_dev(z.MODE_MILLER, ml, g1=g1, g2=g2, stream=st))
 print("          Miller loop only            n=2^%d   %.2f ms   %.3f M/s" % (log2 + 2, ms, n / ms / 1e3))
 ms = timed(lambda: eng.pairing_dev(z.MODE_PAIRING, out, g1=g1, g2=g2, n_checks=nc, pairs_per_check=k, is_one=one, stream=st))
 print("config 3  4-pair product checks       n=2^%d checks   %.2f ms   %.3f M checks/s  (%.3f M pairs/s)" % (log2, ms, nc / ms / 1e3, n / ms / 1e3))
+# config 3 with the three "verifying-key" G2 points of every check prepared once (G2Prepared tables)
+kf = 3
+fixed = g2[:kf].contiguous()
+tab = torch.empty((kf, eng.G2_PREPARED_U64), dtype=torch.int64, device=dev)
+eng.g2_prepare_dev(fixed, kf, tab, stream=st)
+var = g2.view(nc, k, 24)[:, 0, :].contiguous()
+ms = timed(lambda: eng.multi_pairing_prepared_dev(out, g1, var, nc, k, tab, kf, is_one=one, stream=st))
+print("config 3  same, 3 of 4 G2 prepared     n=2^%d checks   %.2f ms   %.3f M checks/s" % (log2, ms, nc / ms / 1e3))
 eng.close()

@@ -40,6 +40,13 @@ SYMBOLS = {
     "zkp_gen_points_dev": (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_size_t,
                                             c_u64p, c_u8p, c_u64p, c_u8p, ctypes.c_void_p]),
     "zkp_gen_points": (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_size_t, c_u64p, c_u8p, c_u64p, c_u8p]),
+    "zkp_g2_prepare_batch": (ctypes.c_int32, [ctypes.c_void_p, c_u64p, ctypes.c_size_t, c_u64p]),
+    "zkp_g2_prepare_dev": (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_int32, c_u64p, ctypes.c_size_t, c_u64p, ctypes.c_void_p, ctypes.c_void_p]),
+    "zkp_multi_pairing_prepared_batch": (ctypes.c_int32, [ctypes.c_void_p, c_u64p, c_u8p, c_u64p, c_u8p, ctypes.c_size_t, ctypes.c_int32,
+                                                          c_u64p, c_u8p, ctypes.c_int32, c_u64p, c_u8p]),
+    "zkp_multi_pairing_prepared_dev": (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_int32, c_u64p, c_u8p, c_u64p, c_u8p, ctypes.c_size_t,
+                                                        ctypes.c_int32, c_u64p, c_u8p, ctypes.c_int32, c_u64p, c_u8p, ctypes.c_void_p,
+                                                        ctypes.c_void_p]),
     "zkp_fp_from_bytes_batch": (ctypes.c_int32, [ctypes.c_void_p, c_u8p, ctypes.c_size_t, c_u64p, c_u8p]),
     "zkp_fp_to_bytes_batch": (ctypes.c_int32, [ctypes.c_void_p, c_u64p, ctypes.c_size_t, c_u8p]),
     "zkp_fp_bytes_dev": (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, c_u8p,

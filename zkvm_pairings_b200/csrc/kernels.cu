@@ -84,6 +84,18 @@ k_gen_points(uint64_t seed, uint64_t first, size_t n, uint64_t *__restrict__ g1,
     gen_g2_one(b, g2 + 24 * i, g2inf + i);
 }
 
+// G2Prepared-style line tables: out = [point][68][3][lane parity] Montgomery Fp
+__global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS)
+k_g2_prepare(const uint64_t *__restrict__ g2, Fp *__restrict__ out, uint32_t *err, size_t n) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    if (i >= n) return;
+    bool bad = false;
+    G2A q;
+    load_g2(q, g2 + 24 * i, bad);
+    g2_prepare(q, out + i * (ZKP_LINE_STEPS * 3 * 2) + lane_par());
+    if (lane_or(bad) && err && lane_par() == 0) atomicOr(err, 1u);
+}
+
 // Group-level batch ops: subgroup/on-curve validation and scalar multiplication.
 // gop = GroupOp; points are 12 (G1) or 24 (G2) u64 each; flag = status (checks) or is_infinity (mul).
 __global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS)
@@ -225,7 +237,7 @@ struct DevBuf {
     }
 };
 
-enum { B_G1 = 0, B_G1INF, B_G2, B_G2INF, B_IN, B_OUT, B_FLAG, B_NBUF };
+enum { B_G1 = 0, B_G1INF, B_G2, B_G2INF, B_IN, B_OUT, B_FLAG, B_TAB, B_NBUF };
 
 struct DevState {
     int id = 0;
@@ -254,11 +266,12 @@ static inline unsigned grid_for(size_t n) { return (unsigned)((2 * n + ZKP_TPB -
 extern "C" size_t zkp_fe_scratch_bytes(size_t n);
 cudaError_t zkp_launch_k_pairing(int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
                                  size_t n, int k, const uint64_t *in12, uint64_t *out, uint8_t *is_one, uint32_t *err,
-                                 void *scratch, cudaStream_t st, int *launches);
+                                 void *scratch, const void *tab, const uint8_t *tabinf, int kf, cudaStream_t st, int *launches);
 
 static cudaError_t launch_pairing(zkp_ctx *ctx, DevState &d, int mode, const uint64_t *g1, const uint8_t *g1inf,
                                   const uint64_t *g2, const uint8_t *g2inf, size_t n, int k, const uint64_t *in12,
-                                  uint64_t *out, uint8_t *is_one, uint32_t *err, cudaStream_t st) {
+                                  uint64_t *out, uint8_t *is_one, uint32_t *err, cudaStream_t st,
+                                  const void *tab = nullptr, const uint8_t *tabinf = nullptr, int kf = 0) {
     if (n == 0) return cudaSuccess;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->timing) {
@@ -273,7 +286,7 @@ static cudaError_t launch_pairing(zkp_ctx *ctx, DevState &d, int mode, const uin
         if (e != cudaSuccess) return e;
     }
     int nl = 0;
-    cudaError_t rc = zkp_launch_k_pairing(mode, g1, g1inf, g2, g2inf, n, k, in12, out, is_one, err, scratch, st, &nl);
+    cudaError_t rc = zkp_launch_k_pairing(mode, g1, g1inf, g2, g2inf, n, k, in12, out, is_one, err, scratch, tab, tabinf, kf, st, &nl);
     ctx->launches += nl;
     if (scratch) cudaFreeAsync(scratch, st);
     if (ctx->timing) {
@@ -518,6 +531,9 @@ static void slice_of(size_t n, size_t ndev, size_t d, size_t &lo, size_t &hi) {
 struct HostJob {
     int mode = 0;   // 1 miller, 2 final exp, 3 pairing ; 16 = tower op ; 32 = gen points ; 48 = group op
     const uint64_t *pts = nullptr, *scalars = nullptr;   // group op inputs (inf in g1inf, outputs in out / flags)
+    const uint64_t *tab = nullptr;                       // prepared G2 line tables shared by all checks (kf of them)
+    const uint8_t *tabinf = nullptr;
+    int kf = 0;
     const uint64_t *g1 = nullptr, *g2 = nullptr, *in12 = nullptr, *a = nullptr, *b = nullptr;
     const uint8_t *g1inf = nullptr, *g2inf = nullptr;
     uint64_t *out = nullptr, *og1 = nullptr, *og2 = nullptr;
@@ -601,20 +617,30 @@ static int32_t run_slice(zkp_ctx *ctx, DevState &d, const HostJob &j, size_t lo,
             CUS(cudaMemcpyAsync(j.og2inf + c0, B[B_G2INF].p, cn, cudaMemcpyDeviceToHost, st));
         } else {
             size_t np = cn * (size_t)j.k, p0 = c0 * (size_t)j.k;
-            const uint8_t *di1 = nullptr, *di2 = nullptr;
+            size_t nq = cn * (size_t)(j.k - j.kf), q0 = c0 * (size_t)(j.k - j.kf);   // per-check G2 points
+            const uint8_t *di1 = nullptr, *di2 = nullptr, *dti = nullptr;
             if (j.mode & 1) {
                 CUS(B[B_G1].ensure(np * 96));
-                CUS(B[B_G2].ensure(np * 192));
+                CUS(B[B_G2].ensure(nq * 192 + 16));
                 CUS(cudaMemcpyAsync(B[B_G1].p, j.g1 + p0 * 12, np * 96, cudaMemcpyHostToDevice, st));
-                CUS(cudaMemcpyAsync(B[B_G2].p, j.g2 + p0 * 24, np * 192, cudaMemcpyHostToDevice, st));
+                if (nq) CUS(cudaMemcpyAsync(B[B_G2].p, j.g2 + q0 * 24, nq * 192, cudaMemcpyHostToDevice, st));
+                if (j.kf) {
+                    size_t tb = (size_t)j.kf * ZKP_LINE_STEPS * 3 * 2 * sizeof(Fp);
+                    CUS(B[B_TAB].ensure(tb + 16));
+                    CUS(cudaMemcpyAsync(B[B_TAB].p, j.tab, tb, cudaMemcpyHostToDevice, st));
+                    if (j.tabinf) {
+                        CUS(cudaMemcpyAsync((uint8_t *)B[B_TAB].p + tb, j.tabinf, j.kf, cudaMemcpyHostToDevice, st));
+                        dti = (const uint8_t *)B[B_TAB].p + tb;
+                    }
+                }
                 if (j.g1inf) {
                     CUS(B[B_G1INF].ensure(np));
                     CUS(cudaMemcpyAsync(B[B_G1INF].p, j.g1inf + p0, np, cudaMemcpyHostToDevice, st));
                     di1 = (const uint8_t *)B[B_G1INF].p;
                 }
-                if (j.g2inf) {
-                    CUS(B[B_G2INF].ensure(np));
-                    CUS(cudaMemcpyAsync(B[B_G2INF].p, j.g2inf + p0, np, cudaMemcpyHostToDevice, st));
+                if (j.g2inf && nq) {
+                    CUS(B[B_G2INF].ensure(nq));
+                    CUS(cudaMemcpyAsync(B[B_G2INF].p, j.g2inf + q0, nq, cudaMemcpyHostToDevice, st));
                     di2 = (const uint8_t *)B[B_G2INF].p;
                 }
             } else {
@@ -625,7 +651,7 @@ static int32_t run_slice(zkp_ctx *ctx, DevState &d, const HostJob &j, size_t lo,
             if (j.flags) CUS(B[B_FLAG].ensure(cn));
             CUS(launch_pairing(ctx, d, j.mode, (const uint64_t *)B[B_G1].p, di1, (const uint64_t *)B[B_G2].p, di2, cn, j.k,
                                (const uint64_t *)B[B_IN].p, (uint64_t *)B[B_OUT].p, j.flags ? (uint8_t *)B[B_FLAG].p : nullptr,
-                               d.d_err, st));
+                               d.d_err, st, j.kf ? B[B_TAB].p : nullptr, dti, j.kf));
             CUS(cudaMemcpyAsync(j.out + c0 * 72, B[B_OUT].p, cn * 576, cudaMemcpyDeviceToHost, st));
             if (j.flags) CUS(cudaMemcpyAsync(j.flags + c0, B[B_FLAG].p, cn, cudaMemcpyDeviceToHost, st));
         }
@@ -720,6 +746,73 @@ int32_t zkp_gen_points(zkp_ctx *ctx, uint64_t seed, uint64_t first, size_t n, ui
     HostJob j;
     j.mode = 32; j.seed = seed; j.first = first; j.og1 = g1; j.og1inf = g1inf; j.og2 = g2; j.og2inf = g2inf;
     return run_host_job(ctx, j, n);
+}
+
+// ---- prepared G2 points
+int32_t zkp_g2_prepare_batch(zkp_ctx *ctx, const uint64_t *g2_xy, size_t n, uint64_t *out_tables) {
+    if (!ctx) return fail(ZKP_ERR_INVALID_ARG, "ctx is NULL");
+    if (n == 0) return ZKP_OK;
+    if (!g2_xy || !out_tables) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState &d = ctx->devs[0];   // a handful of verifying-key points: one device
+    CU(cudaSetDevice(d.id));
+    cudaStream_t st = d.stream[0];
+    DevBuf *B = d.buf[0];
+    const size_t tb = (size_t)ZKP_G2_PREPARED_U64 * 8;
+    CU(cudaMemsetAsync(d.d_err, 0, sizeof(uint32_t), st));
+    CU(B[B_G2].ensure(n * 192));
+    CU(B[B_TAB].ensure(n * tb + 16));
+    CU(cudaMemcpyAsync(B[B_G2].p, g2_xy, n * 192, cudaMemcpyHostToDevice, st));
+    k_g2_prepare<<<grid_for(n), ZKP_TPB, 0, st>>>((const uint64_t *)B[B_G2].p, (Fp *)B[B_TAB].p, d.d_err, n);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_tables, B[B_TAB].p, n * tb, cudaMemcpyDeviceToHost, st));
+    uint32_t herr = 0;
+    CU(cudaMemcpyAsync(&herr, d.d_err, sizeof herr, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (herr & 1) return fail(ZKP_ERR_NONCANONICAL, "input limb vector >= p (non-canonical field element)");
+    return ZKP_OK;
+}
+int32_t zkp_g2_prepare_dev(zkp_ctx *ctx, int32_t dev, const uint64_t *d_g2_xy, size_t n, uint64_t *d_out_tables, uint32_t *d_err, void *stream) {
+    int32_t rc = check_dev(ctx, dev);
+    if (rc) return rc;
+    if (n && (!d_g2_xy || !d_out_tables)) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState &d = ctx->devs[dev];
+    CU(cudaSetDevice(d.id));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
+    if (n) {
+        k_g2_prepare<<<grid_for(n), ZKP_TPB, 0, st>>>(d_g2_xy, (Fp *)d_out_tables, d_err, n);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    return ZKP_OK;
+}
+int32_t zkp_multi_pairing_prepared_batch(zkp_ctx *ctx, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
+                                         size_t n_checks, int32_t k, const uint64_t *tables, const uint8_t *tables_inf, int32_t kf,
+                                         uint64_t *out, uint8_t *is_one) {
+    if (k < 1 || kf < 0 || kf > k) return fail(ZKP_ERR_INVALID_ARG, "need 0 <= prepared pairs <= pairs_per_check");
+    if (k > ZKP_MAX_PAIRS_PER_CHECK) return fail(ZKP_ERR_TOO_MANY_PAIRS, "pairs_per_check > 8");
+    if (n_checks && (!g1 || !out || (kf < k && !g2) || (kf && !tables))) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
+    HostJob j;
+    j.mode = 3; j.g1 = g1; j.g1inf = g1inf; j.g2 = g2; j.g2inf = g2inf; j.k = k; j.out = out; j.flags = is_one;
+    j.tab = tables; j.tabinf = tables_inf; j.kf = kf;
+    return run_host_job(ctx, j, n_checks);
+}
+int32_t zkp_multi_pairing_prepared_dev(zkp_ctx *ctx, int32_t dev, const uint64_t *d_g1, const uint8_t *d_g1inf, const uint64_t *d_g2,
+                                       const uint8_t *d_g2inf, size_t n_checks, int32_t k, const uint64_t *d_tables,
+                                       const uint8_t *d_tables_inf, int32_t kf, uint64_t *d_out, uint8_t *d_is_one, uint32_t *d_err,
+                                       void *stream) {
+    int32_t rc = check_dev(ctx, dev);
+    if (rc) return rc;
+    if (k < 1 || kf < 0 || kf > k || k > ZKP_MAX_PAIRS_PER_CHECK) return fail(ZKP_ERR_INVALID_ARG, "bad pairs_per_check / prepared count");
+    if (!d_g1 || !d_out || (kf < k && !d_g2) || (kf && !d_tables)) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevState &d = ctx->devs[dev];
+    CU(cudaSetDevice(d.id));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
+    CU(launch_pairing(ctx, d, 3, d_g1, d_g1inf, d_g2, d_g2inf, n_checks, k, nullptr, d_out, d_is_one, d_err, st, d_tables, d_tables_inf, kf));
+    return ZKP_OK;
 }
 
 // bytes <-> limbs on device-resident buffers (dir 0: from_bytes, 1: to_bytes)

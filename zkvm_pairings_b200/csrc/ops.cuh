@@ -173,18 +173,26 @@ enum { ZKP_DO_MILLER = 1, ZKP_DO_FINAL_EXP = 2 };
 // (k <= K) so the per-thread scratch is sized for the common k = 1 case.
 template <int K>
 ZKP_HD void pairing_front(Fp12 &f, bool &bad, int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2,
-                          const uint8_t *g2inf, int k, const uint64_t *in12) {
+                          const uint8_t *g2inf, int k, const uint64_t *in12, const Fp *tab = nullptr,
+                          const uint8_t *tabinf = nullptr, int kf = 0) {
+    // k pairs in total; the last kf of them take their G2 lines from the prepared tables `tab`
+    // (then g2 / g2inf hold only the k - kf per-check points)
     if (mode & ZKP_DO_MILLER) {
         G1A ps[K];
         G2A qs[K];
         G2P rs[K];
         bool skip[K];
+        const int kv = k - kf;
         for (int j = 0; j < k; j++) {
             load_g1(ps[j], g1 + 12 * j, bad);
-            load_g2(qs[j], g2 + 24 * j, bad);
-            skip[j] = (g1inf && g1inf[j]) | (g2inf && g2inf[j]);
+            skip[j] = g1inf && g1inf[j];
         }
-        miller_loop(f, ps, qs, skip, rs, k);
+        for (int j = 0; j < kv; j++) {
+            load_g2(qs[j], g2 + 24 * j, bad);
+            skip[j] = skip[j] | (g2inf && g2inf[j]);
+        }
+        for (int j = 0; j < kf; j++) skip[kv + j] = skip[kv + j] | (tabinf && tabinf[j]);
+        miller_loop(f, ps, qs, skip, rs, kv, tab, kf);
     } else {
         load_fp12(f, in12, bad);
     }

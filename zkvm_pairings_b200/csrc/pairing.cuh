@@ -78,36 +78,76 @@ ZKP_HD void ell(Fp12 &f, const Fp2 *co, const G1A &p, bool skip) {
 // Bits of |x| >> 1 below its leading one (bit 62), MSB first: 62 iterations, additions where set.
 #define ZKP_X_HALF (ZKP_BLS_X >> 1)
 
-// Miller loop over k pairs sharing the accumulator f (k = 1: single pairing).  Pairs flagged
-// `skip` (a point at infinity) contribute one.  Output is conjugated (x < 0).  rs = k scratch G2P.
-ZKP_HD void miller_loop(Fp12 &f, const G1A *ps, const G2A *qs, const bool *skip, G2P *rs, int k) {
+// Prepared G2 points ("G2Prepared" of the zkcrypto lineage): the 68 line-coefficient
+// triples the loop below derives from Q (63 doubling + 5 addition steps), computed once for points
+// that stay fixed across checks (verifying-key points).  Device format: Montgomery limbs,
+// [point][step][coefficient][lane parity] Fp, so each lane fetches its own half with three 128-bit
+// loads and all checks of a warp read the same addresses (one broadcast per load).
+#define ZKP_LINE_STEPS 68
+ZKP_HD Fp2 line_tab_load(const Fp *tab, int point, int step, int c) {
+    Fp2 r;
+    r.c = tab[((point * ZKP_LINE_STEPS + step) * 3 + c) * 2 + lane_par()];
+    return r;
+}
+
+// Miller loop over kv + kf pairs sharing the accumulator f (one pair: single pairing).  The first kv
+// pairs bring their own G2 point (qs, scratch rs), the last kf use prepared line tables.  Pairs
+// flagged `skip` (a point at infinity) contribute one.  Output is conjugated (x < 0).
+ZKP_HD void miller_loop(Fp12 &f, const G1A *ps, const G2A *qs, const bool *skip, G2P *rs, int kv,
+                        const Fp *tab = nullptr, int kf = 0) {
     Fp2 co[3];
     fp12_set_one(f);
-    for (int j = 0; j < k; j++) {
+    for (int j = 0; j < kv; j++) {
         rs[j].x = qs[j].x;
         rs[j].y = qs[j].y;
         rs[j].z = fp2_one();
     }
+    int step = 0;
 #pragma unroll 1
-    for (int b = 61; b >= 0; b--) {
-        bool bit = (ZKP_X_HALF >> b) & 1;
-        for (int j = 0; j < k; j++) {
+    for (int b = 61; b >= -1; b--) {   // b = -1: the final doubling step, no squaring after it
+        bool bit = b >= 0 && ((ZKP_X_HALF >> b) & 1);
+        for (int j = 0; j < kv; j++) {
             doubling_step(rs[j], co);
             ell(f, co, ps[j], skip[j]);
         }
+        for (int j = 0; j < kf; j++) {
+            for (int c = 0; c < 3; c++) co[c] = line_tab_load(tab, j, step, c);
+            ell(f, co, ps[kv + j], skip[kv + j]);
+        }
+        step++;
         if (bit) {
-            for (int j = 0; j < k; j++) {
+            for (int j = 0; j < kv; j++) {
                 addition_step(rs[j], qs[j], co);
                 ell(f, co, ps[j], skip[j]);
             }
+            for (int j = 0; j < kf; j++) {
+                for (int c = 0; c < 3; c++) co[c] = line_tab_load(tab, j, step, c);
+                ell(f, co, ps[kv + j], skip[kv + j]);
+            }
+            step++;
         }
-        fp12_sqr(f, f);
-    }
-    for (int j = 0; j < k; j++) {
-        doubling_step(rs[j], co);
-        ell(f, co, ps[j], skip[j]);
+        if (b >= 0) fp12_sqr(f, f);
     }
     fp12_conj(f, f);
+}
+// the line table of one G2 point: this lane's half of the 68 x 3 coefficients, in loop order
+ZKP_HD void g2_prepare(const G2A &q, Fp *out_lane /* stride 2 Fp per coefficient */) {
+    Fp2 co[3];
+    G2P r;
+    r.x = q.x; r.y = q.y; r.z = fp2_one();
+    int step = 0;
+#pragma unroll 1
+    for (int b = 61; b >= -1; b--) {
+        bool bit = b >= 0 && ((ZKP_X_HALF >> b) & 1);
+        doubling_step(r, co);
+        for (int c = 0; c < 3; c++) out_lane[(step * 3 + c) * 2] = co[c].c;
+        step++;
+        if (bit) {
+            addition_step(r, q, co);
+            for (int c = 0; c < 3; c++) out_lane[(step * 3 + c) * 2] = co[c].c;
+            step++;
+        }
+    }
 }
 
 // f^|x| followed by conjugation (x < 0); f in the cyclotomic subgroup.  63 squarings + 5 muls.

@@ -41,15 +41,15 @@ __global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS)
 k_pairing(int mode, const uint64_t *__restrict__ g1, const uint8_t *__restrict__ g1inf,
           const uint64_t *__restrict__ g2, const uint8_t *__restrict__ g2inf, int k,
           const uint64_t *__restrict__ in12, uint64_t *__restrict__ out, uint8_t *__restrict__ is_one,
-          uint32_t *err, size_t n, FeScratch fs) {
+          uint32_t *err, size_t n, FeScratch fs, const Fp *__restrict__ tab, const uint8_t *__restrict__ tabinf, int kf) {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     bool live = i < n;
     if (!live) i = n - 1;   // stay converged: redo the last element, store nothing
-    size_t e = i * (size_t)k;
+    size_t e = i * (size_t)k, e2 = i * (size_t)(k - kf);   // the last kf pairs of a check use prepared G2 tables
     bool bad = false;
     Fp12 f;
-    pairing_front<K>(f, bad, mode, g1 ? g1 + 12 * e : nullptr, g1inf ? g1inf + e : nullptr, g2 ? g2 + 24 * e : nullptr,
-                     g2inf ? g2inf + e : nullptr, k, in12 ? in12 + 72 * i : nullptr);
+    pairing_front<K>(f, bad, mode, g1 ? g1 + 12 * e : nullptr, g1inf ? g1inf + e : nullptr, g2 ? g2 + 24 * e2 : nullptr,
+                     g2inf ? g2inf + e2 : nullptr, k, in12 ? in12 + 72 * i : nullptr, tab, tabinf, kf);
     if (mode & ZKP_DO_FINAL_EXP) {
         FeState s;
         Fp nrm = fe_prepare(s, f);
@@ -105,17 +105,17 @@ static int pair_capacity(int k) { return k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : 
 // `scratch`: zkp_fe_scratch_bytes(n) device bytes when mode has bit1 set (else unused)
 cudaError_t zkp_launch_k_pairing(int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
                                  size_t n, int k, const uint64_t *in12, uint64_t *out, uint8_t *is_one, uint32_t *err,
-                                 void *scratch, cudaStream_t st, int *launches) {
+                                 void *scratch, const void *tab, const uint8_t *tabinf, int kf, cudaStream_t st, int *launches) {
     if (n == 0) return cudaSuccess;
     FeScratch fs;
     fs.lanes = (Fp *)scratch;
     fs.norm = fs.lanes ? fs.lanes + 2 * n * ZKP_FE_LANE_FP : nullptr;
     dim3 g((unsigned)((2 * n + ZKP_TPB - 1) / ZKP_TPB)), b(ZKP_TPB);
     switch (pair_capacity(k)) {
-        case 1: k_pairing<1><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs); break;
-        case 2: k_pairing<2><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs); break;
-        case 4: k_pairing<4><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs); break;
-        default: k_pairing<8><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs); break;
+        case 1: k_pairing<1><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
+        case 2: k_pairing<2><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
+        case 4: k_pairing<4><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
+        default: k_pairing<8><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
     }
     *launches = 1;
     if (mode & ZKP_DO_FINAL_EXP) {

@@ -222,6 +222,46 @@ class PairingEngine:
         self._check(self._lib.zkp_gen_points(self._ctx, seed, first, n, _ptr(g1), _ptr(i1), _ptr(g2), _ptr(i2)))
         return g1, i1, g2, i2
 
+    # ------------------------------------------------------------------ prepared G2 points
+    G2_PREPARED_U64 = 68 * 3 * 12
+
+    def g2_prepare_batch(self, g2):
+        """Line tables ("G2Prepared") of fixed G2 points -> (n, 2448) uint64, opaque internal format."""
+        pts, _, n = self._pts(g2, 24, None)
+        out = np.empty((n, self.G2_PREPARED_U64), np.uint64)
+        self._check(self._lib.zkp_g2_prepare_batch(self._ctx, _ptr(pts), n, _ptr(out)))
+        return out
+
+    def multi_pairing_prepared_batch(self, g1, g2, pairs_per_check: int, tables, g1_inf=None, g2_inf=None, tables_inf=None):
+        """Like multi_pairing_batch, with the LAST len(tables) pairs of every check taking their G2 point from
+        prepared tables shared by all checks; g2 holds only the per-check points."""
+        tables = np.ascontiguousarray(tables, dtype=np.uint64).reshape(-1, self.G2_PREPARED_U64)
+        kf, k = tables.shape[0], pairs_per_check
+        g1, i1, n1 = self._pts(g1, 12, g1_inf)
+        if k < 1 or kf > k or n1 % k:
+            raise ValueError("bad pairs_per_check / number of G1 points")
+        nc = n1 // k
+        if kf < k:
+            g2, i2, n2 = self._pts(g2, 24, g2_inf)
+            if n2 != nc * (k - kf):
+                raise ValueError("expected n_checks * (pairs_per_check - prepared) G2 points")
+        else:
+            g2, i2 = None, None
+        ti = None if tables_inf is None else np.ascontiguousarray(tables_inf, dtype=np.uint8).reshape(kf)
+        out, is_one = np.empty((nc, 72), np.uint64), np.zeros(nc, np.uint8)
+        self._check(self._lib.zkp_multi_pairing_prepared_batch(self._ctx, _ptr(g1), _ptr(i1), _ptr(g2), _ptr(i2), nc, k, _ptr(tables),
+                                                               _ptr(ti), kf, _ptr(out), _ptr(is_one)))
+        return out, is_one
+
+    def g2_prepare_dev(self, d_g2, n: int, d_tables, err=None, stream: int = 0, dev: int = 0):
+        self._check(self._lib.zkp_g2_prepare_dev(self._ctx, dev, _dptr(d_g2), n, _dptr(d_tables), _dptr(err), ctypes.c_void_p(stream)))
+
+    def multi_pairing_prepared_dev(self, out, g1, g2, n_checks: int, pairs_per_check: int, d_tables, prepared_pairs: int, g1_inf=None,
+                                   g2_inf=None, tables_inf=None, is_one=None, err=None, stream: int = 0, dev: int = 0):
+        self._check(self._lib.zkp_multi_pairing_prepared_dev(self._ctx, dev, _dptr(g1), _dptr(g1_inf), _dptr(g2), _dptr(g2_inf), n_checks,
+                                                             pairs_per_check, _dptr(d_tables), _dptr(tables_inf), prepared_pairs,
+                                                             _dptr(out), _dptr(is_one), _dptr(err), ctypes.c_void_p(stream)))
+
     # ------------------------------------------------------------------ byte (de)serialisation (SURVEY 8f)
     def fp_from_bytes_batch(self, data):
         """Fp::from_bytes (src/fp.rs:165-191): (n,48) big-endian bytes -> (limbs (n,6) uint64, ok (n,) uint8)."""
