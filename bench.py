@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--log2-batch", type=int, default=20, help="pairings per GPU per step = 2^this")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-seconds", type=float, default=None, help="--impl reference: CPU seconds per step (default: bounded by the step count)")
     return ap.parse_args()
 
 
@@ -99,7 +100,7 @@ def run_reference(args):
     cores = coracle.ncores()
     rate0, _ = cpu_oracle_rate(8 * cores, cores)
     # bounded sample per step so that (steps + warmup) stays within a few minutes
-    per_step_s = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    per_step_s = args.ref_seconds if args.ref_seconds else max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
     n = max(cores, min(1 << 16, int(rate0 * per_step_s)))
     for _ in range(args.warmup):
         cpu_oracle_rate(n, cores)
@@ -177,6 +178,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import zkvm_pairings_b200 as z
+    from zkvm_pairings_b200 import sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -211,7 +213,7 @@ def run_ours(args):
     i2 = torch.empty(n, dtype=torch.uint8, device=dev)
     out = torch.empty((n, 72), dtype=torch.int64, device=dev)
     err = torch.zeros(1, dtype=torch.int32, device=dev)
-    eng.gen_points_dev(0x5EED5EED, rank * n, n, g1, i1, g2, i2, stream=st)
+    eng.gen_points_dev(0x5EED5EED, sharding.synthetic_first_index(rank, n), n, g1, i1, g2, i2, stream=st)
     torch.cuda.synchronize()
 
     # ---- integer-multiply roofline denominators, measured in this run
@@ -238,11 +240,8 @@ def run_ours(args):
     launches = eng.launch_count - launches0
     clocks = sampler.stop() if sampler else None
     assert int(err.item()) == 0, "non-canonical synthetic input?"
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    max_ms = float(t.item())
-    value = world * n * args.steps / (max_ms * 1e-3)
+    max_ms = sharding.max_over_ranks(total_ms, world, dev)
+    value = sharding.whole_job_rate(n, args.steps, world, max_ms)
 
     # ---- end to end through the host-buffer C-ABI call, pinned host memory, copies in the timed region
     e2e_n = n
@@ -270,10 +269,7 @@ def run_ours(args):
         e2e_step()
     barrier()
     e2e_dt = time.perf_counter() - t0
-    te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_n * e2e_steps / float(te.item())
+    e2e_value = sharding.whole_job_rate(e2e_n, e2e_steps, world, 1e3 * sharding.max_over_ranks(e2e_dt, world, dev))
     # the e2e result must equal the device-resident result (same inputs)
     same = bool(torch.equal(h_out[:4096], out[:4096].cpu()))
 
