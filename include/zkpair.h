@@ -65,12 +65,15 @@ enum zkp_tower_op {
     ZKP_OP_FP_MUL = 3,        /* Fp::mul            src/fp.rs:413-434 */
     ZKP_OP_FP_SQR = 4,        /* Fp::square         src/fp.rs:452-455 */
     ZKP_OP_FP_INV = 5,        /* Fp::invert         src/fp.rs:306-319 (status bit1 set for zero) */
+    ZKP_OP_FP_POW = 6,        /* Fp::pow_vartime    src/fp.rs:264-276; b = exponent, six RAW little-endian u64 */
+    ZKP_OP_FP_SQRT = 7,       /* Fp::sqrt           src/fp.rs:280-300 (status bit1 set for a non-residue = Err(())) */
     ZKP_OP_FP2_ADD = 16, ZKP_OP_FP2_SUB = 17, ZKP_OP_FP2_NEG = 18,
     ZKP_OP_FP2_MUL = 19,      /* src/fp2.rs:192-209 */
     ZKP_OP_FP2_SQR = 20,      /* src/fp2.rs:171-189 */
     ZKP_OP_FP2_INV = 21,      /* src/fp2.rs:278-296 */
     ZKP_OP_FP2_MUL_NR = 22,   /* mul_by_nonresidue  src/fp2.rs:161-168 */
     ZKP_OP_FP2_CONJ = 23,     /* conjugate = frobenius_map  src/fp2.rs:147-157 */
+    ZKP_OP_FP2_POW = 24,      /* Fp2::pow_vartime   src/fp2.rs:301-313; b = exponent, six raw u64 */
     ZKP_OP_FP6_ADD = 32, ZKP_OP_FP6_SUB = 33, ZKP_OP_FP6_NEG = 34,
     ZKP_OP_FP6_MUL = 35,      /* src/fp6.rs:188-267 */
     ZKP_OP_FP6_SQR = 36,      /* src/fp6.rs:274-288 */
@@ -89,7 +92,8 @@ enum zkp_tower_op {
     ZKP_OP_FP12_CYC_SQR = 57, /* Granger-Scott cyclotomic squaring */
     ZKP_OP_FP12_CYC_EXP = 58, /* f^x for the curve parameter x (negative): conj(f^|x|) */
     ZKP_OP_FP12_FROB2 = 59,   /* a^(p^2) */
-    ZKP_OP_FP12_FROB3 = 60    /* a^(p^3) */
+    ZKP_OP_FP12_FROB3 = 60,   /* a^(p^3) */
+    ZKP_OP_FP12_POW = 61      /* Fp12::pow_vartime  src/fp12.rs:127-139; b = exponent, six raw u64 */
 };
 
 typedef struct zkp_ctx zkp_ctx;

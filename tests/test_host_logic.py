@@ -98,6 +98,7 @@ def test_op_widths():
     assert op_widths("fp_mul") == (1, 1, 1) and op_widths("fp_inv") == (1, 0, 1)
     assert op_widths("fp12_mul_by_014") == (12, 6, 12) and op_widths("fp6_mul_by_01") == (6, 4, 6)
     assert op_widths("fp12_frob2") == (12, 0, 12) and op_widths("fp2_mul_nr") == (2, 0, 2)
+    assert op_widths("fp12_pow") == (12, 1, 12) and op_widths("fp_sqrt") == (1, 0, 1)
 
 
 # ---------------------------------------------------------------- dev simulation of the device code
@@ -113,10 +114,21 @@ def sim():
     return ctypes.CDLL(so)
 
 
-def test_sim_tower_ops_bit_exact(sim, coracle):
+def test_sim_tower_ops_bit_exact(sim, coracle, pyref):
     from zkvm_pairings_b200 import TOWER_OPS, op_widths
     for name, code in TOWER_OPS.items():
         na, nb, nr = op_widths(name)
+        if name in util.POW_OPS:
+            n = {"fp_pow": 8, "fp2_pow": 6, "fp12_pow": 2, "fp_sqrt": 8}[name]
+            a, b, exp, exp_status = util.pow_sqrt_case(pyref, name, n, seed=code)
+            out, st = np.zeros((n, 6 * nr), np.uint64), np.zeros(n, np.uint8)
+            sim.sim_tower_op(code, _p(a), _p(b), _p(out), _p(st), ctypes.c_size_t(n))
+            assert np.array_equal(st, exp_status), name
+            if name == "fp_sqrt":
+                assert all(r is None or g in (r, pyref.P - r) for g, r in zip(util.arr_fp(out), exp))
+            else:
+                assert np.array_equal(out, exp), name
+            continue
         n = 14
         a = util.random_fp_matrix(n, na, seed=code + 1)
         b = util.random_fp_matrix(n, nb, seed=code + 101) if nb else None

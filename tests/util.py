@@ -160,3 +160,40 @@ def random_scalars(n, seed, edges=True):
     vals = [0, 1, 2, 3, R_ORDER - 1, R_ORDER, (1 << 256) - 1] if edges else []
     vals = vals[:n] + [rng.getrandbits(256) for _ in range(max(0, n - len(vals)))]
     return np.array([[(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)] for v in vals[:n]], dtype=np.uint64)
+
+
+POW_OPS = ("fp_pow", "fp2_pow", "fp12_pow", "fp_sqrt")
+
+
+def pow_sqrt_case(pyref, name, n, seed):
+    """Operands and expected results (via the Python oracle) for the ops the C oracle has no entry for:
+    pow_vartime (src/fp.rs:264-276, src/fp2.rs:301-313, src/fp12.rs:127-139; exponent = six raw u64 limbs,
+    edge exponents 0, 1, 2, p, 2^384-1 first) and Fp::sqrt (src/fp.rs:280-300; the reference's KAT
+    sqrt(300855555557) and its non-residue 72057594037927816 first)."""
+    import random
+    rng = random.Random(seed)
+    P = pyref.P
+    if name == "fp_sqrt":
+        vals = [300855555557, 72057594037927816, 0, 1, 4] + [rng.randrange(P) for _ in range(max(0, n - 5))]
+        vals = vals[:n]
+        a = fp_arr(vals).reshape(-1, 6)
+        roots = [pyref.fp_sqrt(v) for v in vals]
+        exp_status = np.array([2 if r is None else 0 for r in roots], np.uint8)
+        return a, None, roots, exp_status
+    width = {"fp_pow": 1, "fp2_pow": 2, "fp12_pow": 12}[name]
+    a = random_fp_matrix(n, width, seed=seed, edges=False)
+    es = [0, 1, 2, P, (1 << 384) - 1] + [rng.getrandbits(384) for _ in range(max(0, n - 5))]
+    es = es[:n]
+    b = np.array([[(e >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(6)] for e in es], dtype=np.uint64)
+    exp = []
+    for row, e in zip(a, es):
+        by = [(e >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(6)]
+        if name == "fp_pow":
+            exp.append(fp_arr([pyref.fp_pow_vartime(arr_fp(row)[0], by)]).reshape(-1))
+        elif name == "fp2_pow":
+            v = arr_fp(row)
+            r = pyref.fp2_pow_vartime((v[0], v[1]), by)
+            exp.append(fp_arr([r[0], r[1]]).reshape(-1))
+        else:
+            exp.append(fp12_to_arr(pyref.fp12_pow_vartime(arr_to_fp12(row), by)))
+    return a, b, np.stack(exp), np.zeros(n, np.uint8)

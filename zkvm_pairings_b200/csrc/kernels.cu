@@ -694,8 +694,8 @@ static int32_t run_host_job(zkp_ctx *ctx, const HostJob &j, size_t n) {
 int32_t zkp_tower_op_batch(zkp_ctx *ctx, int32_t op, const uint64_t *a, const uint64_t *b, uint64_t *out, uint8_t *status, size_t n) {
     int na, nb, nr;
     tower_op_shape(op, na, nb, nr);
-    bool known = (op >= 0 && op <= OP_FP_INV) || (op >= OP_FP2_ADD && op <= OP_FP2_CONJ) || (op >= OP_FP6_ADD && op <= OP_FP6_MUL_BY_01) ||
-                 (op >= OP_FP12_ADD && op <= OP_FP12_FROB3);
+    bool known = (op >= 0 && op <= OP_FP_SQRT) || (op >= OP_FP2_ADD && op <= OP_FP2_POW) || (op >= OP_FP6_ADD && op <= OP_FP6_MUL_BY_01) ||
+                 (op >= OP_FP12_ADD && op <= OP_FP12_POW);
     if (!known) return fail(ZKP_ERR_INVALID_ARG, "unknown tower op");
     if (n && (!a || !out || (nb && !b))) return fail(ZKP_ERR_INVALID_ARG, "NULL operand");
     HostJob j;

@@ -14,11 +14,11 @@ namespace zkp {
 
 // op codes of the element-wise tower entry point (zkp_tower_op_batch)
 enum TowerOp {
-    OP_FP_ADD = 0, OP_FP_SUB, OP_FP_NEG, OP_FP_MUL, OP_FP_SQR, OP_FP_INV,
-    OP_FP2_ADD = 16, OP_FP2_SUB, OP_FP2_NEG, OP_FP2_MUL, OP_FP2_SQR, OP_FP2_INV, OP_FP2_MUL_NR, OP_FP2_CONJ,
+    OP_FP_ADD = 0, OP_FP_SUB, OP_FP_NEG, OP_FP_MUL, OP_FP_SQR, OP_FP_INV, OP_FP_POW, OP_FP_SQRT,
+    OP_FP2_ADD = 16, OP_FP2_SUB, OP_FP2_NEG, OP_FP2_MUL, OP_FP2_SQR, OP_FP2_INV, OP_FP2_MUL_NR, OP_FP2_CONJ, OP_FP2_POW,
     OP_FP6_ADD = 32, OP_FP6_SUB, OP_FP6_NEG, OP_FP6_MUL, OP_FP6_SQR, OP_FP6_INV, OP_FP6_MUL_NR, OP_FP6_FROB, OP_FP6_MUL_BY_1, OP_FP6_MUL_BY_01,
     OP_FP12_ADD = 48, OP_FP12_SUB, OP_FP12_NEG, OP_FP12_MUL, OP_FP12_SQR, OP_FP12_INV, OP_FP12_CONJ, OP_FP12_FROB, OP_FP12_MUL_BY_014, OP_FP12_CYC_SQR, OP_FP12_CYC_EXP,
-    OP_FP12_FROB2 = 59, OP_FP12_FROB3 = 60
+    OP_FP12_FROB2 = 59, OP_FP12_FROB3 = 60, OP_FP12_POW = 61
 };
 
 // number of Fp in operand a / operand b / result for an op (0 = operand unused)
@@ -30,6 +30,7 @@ ZKP_HOSTDEV void tower_op_shape(int op, int &na, int &nb, int &nr) {
         case OP_FP2_ADD: case OP_FP2_SUB: case OP_FP2_MUL:
         case OP_FP6_ADD: case OP_FP6_SUB: case OP_FP6_MUL:
         case OP_FP12_ADD: case OP_FP12_SUB: case OP_FP12_MUL: nb = w; break;
+        case OP_FP_POW: case OP_FP2_POW: case OP_FP12_POW: nb = 1; break;   // b = the exponent: six RAW u64 limbs
         case OP_FP6_MUL_BY_1: nb = 2; break;
         case OP_FP6_MUL_BY_01: nb = 4; break;
         case OP_FP12_MUL_BY_014: nb = 6; break;
@@ -82,8 +83,13 @@ ZKP_HD uint8_t tower_op_one(int op, const uint64_t *a, const uint64_t *b, uint64
     bool bad = false, noinv = false;
     if (op < 16) {   // Fp-level: both lanes compute the same value, the even lane stores it
         Fp x = load_fp(a, bad), y = fp_zero(), r = fp_zero();
-        if (nb) y = load_fp(b, bad);
+        if (nb && op != OP_FP_POW) y = load_fp(b, bad);
         switch (op) {
+            case OP_FP_POW: r = fp_pow(x, b); break;
+            case OP_FP_SQRT: {   // src/fp.rs:280-300: a^((p+1)/4), Err when that is not a root
+                r = fp_pow_const(x, ZKP_SQRT_EXP);
+                noinv = !fp_is_zero(fp_sub(fsqr(r), x));
+            } break;
             case OP_FP_ADD: r = fp_add(x, y); break;
             case OP_FP_SUB: r = fp_sub(x, y); break;
             case OP_FP_NEG: r = fp_neg(x); break;
@@ -98,8 +104,24 @@ ZKP_HD uint8_t tower_op_one(int op, const uint64_t *a, const uint64_t *b, uint64
     Fp12 A, B, R;
     Fp2 *a2 = &A.c0.c0, *b2 = &B.c0.c0, *r2 = &R.c0.c0;
     load_fp2s(a2, a, na / 2, bad);
-    if (nb) load_fp2s(b2, b, nb / 2, bad);
+    const bool is_pow = op == OP_FP2_POW || op == OP_FP12_POW;
+    if (nb && !is_pow) load_fp2s(b2, b, nb / 2, bad);
     switch (op) {
+        case OP_FP2_POW: {       // src/fp2.rs:301-313
+            Fp2 res = fp2_one();
+            for (int i = 383; i >= 0; i--) {
+                res = fp2_sqr(res);
+                if ((b[i >> 6] >> (i & 63)) & 1) res = fp2_mul(res, a2[0]);
+            }
+            r2[0] = res;
+        } break;
+        case OP_FP12_POW: {      // src/fp12.rs:127-139
+            fp12_set_one(R);
+            for (int i = 383; i >= 0; i--) {
+                fp12_sqr(R, R);
+                if ((b[i >> 6] >> (i & 63)) & 1) fp12_mul(R, R, A);
+            }
+        } break;
         case OP_FP2_ADD: r2[0] = fp2_add(a2[0], b2[0]); break;
         case OP_FP2_SUB: r2[0] = fp2_sub(a2[0], b2[0]); break;
         case OP_FP2_NEG: r2[0] = fp2_neg(a2[0]); break;

@@ -40,6 +40,25 @@ ZKP_NOINLINE Fp fp_inv(Fp a) {
     return res;
 }
 
+// a^e for a 384-bit exponent given as six little-endian u64 limbs: Fp::pow_vartime, src/fp.rs:264-276
+ZKP_NOINLINE Fp fp_pow(Fp a, const uint64_t *e) {
+    Fp res = fp_one();
+    for (int i = 383; i >= 0; i--) {
+        res = fsqr(res);
+        if ((e[i >> 6] >> (i & 63)) & 1) res = fmul(res, a);
+    }
+    return res;
+}
+// same with the exponent as twelve constant 32-bit words
+ZKP_NOINLINE Fp fp_pow_const(Fp a, const uint32_t *e) {
+    Fp res = fp_one();
+    for (int i = 383; i >= 0; i--) {
+        res = fsqr(res);
+        if ((e[i >> 5] >> (i & 31)) & 1) res = fmul(res, a);
+    }
+    return res;
+}
+
 // ------------------------------------------------------------------ Fp2 (split over a lane pair)
 //
 // An Fp2 value a0 + a1*u lives in TWO adjacent lanes: the even lane holds a0, the odd lane a1.

@@ -17,16 +17,17 @@ import numpy as np
 from . import _lib
 
 TOWER_OPS = {
-    "fp_add": 0, "fp_sub": 1, "fp_neg": 2, "fp_mul": 3, "fp_sqr": 4, "fp_inv": 5,
+    "fp_add": 0, "fp_sub": 1, "fp_neg": 2, "fp_mul": 3, "fp_sqr": 4, "fp_inv": 5, "fp_pow": 6, "fp_sqrt": 7,
     "fp2_add": 16, "fp2_sub": 17, "fp2_neg": 18, "fp2_mul": 19, "fp2_sqr": 20, "fp2_inv": 21,
-    "fp2_mul_nr": 22, "fp2_conj": 23,
+    "fp2_mul_nr": 22, "fp2_conj": 23, "fp2_pow": 24,
     "fp6_add": 32, "fp6_sub": 33, "fp6_neg": 34, "fp6_mul": 35, "fp6_sqr": 36, "fp6_inv": 37,
     "fp6_mul_nr": 38, "fp6_frob": 39, "fp6_mul_by_1": 40, "fp6_mul_by_01": 41,
     "fp12_add": 48, "fp12_sub": 49, "fp12_neg": 50, "fp12_mul": 51, "fp12_sqr": 52, "fp12_inv": 53,
     "fp12_conj": 54, "fp12_frob": 55, "fp12_mul_by_014": 56, "fp12_cyc_sqr": 57, "fp12_cyc_exp": 58,
-    "fp12_frob2": 59, "fp12_frob3": 60,
+    "fp12_frob2": 59, "fp12_frob3": 60, "fp12_pow": 61,
 }
-_B_WIDTH = {"fp6_mul_by_1": 2, "fp6_mul_by_01": 4, "fp12_mul_by_014": 6}
+# operand b that is not of the same shape as a: sparse multipliers, and the RAW six-limb exponent of pow
+_B_WIDTH = {"fp6_mul_by_1": 2, "fp6_mul_by_01": 4, "fp12_mul_by_014": 6, "fp_pow": 1, "fp2_pow": 1, "fp12_pow": 1}
 _BINARY = {"add", "sub", "mul"}
 
 MODE_MILLER, MODE_FINAL_EXP, MODE_PAIRING = 1, 2, 3
