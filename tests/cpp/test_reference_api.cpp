@@ -1,0 +1,325 @@
+// Runs on the GPU through include/zkpair.hpp (the C++ mirror of the reference crate's API) and is written
+// to read like the crate's own unit tests:
+//   Fp    src/fp.rs:474-610      Fp2   src/fp2.rs:332-485     Fp6  src/fp6.rs:413-560     Fp12 src/fp12.rs:294-410
+//   G1    src/g1.rs:215-341      G2    src/g2.rs:264-443
+// plus the checks SURVEY 8d config 1 asks of the module the crate leaves empty (src/pairings.rs):
+// e(G1gen, G2gen) against the published vector, bilinearity, e^r = 1, multi-Miller = product of Millers.
+// Known answers come from tests/golden/*.json through the generated _kats.inc (tests/test_cpp_api.py).
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+
+#include "zkpair.hpp"
+
+using namespace zkp;
+
+static int g_checks = 0;
+#define ASSERT(cond)                                                            \
+    do {                                                                        \
+        ++g_checks;                                                             \
+        if (!(cond)) {                                                          \
+            std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+            std::exit(1);                                                       \
+        }                                                                       \
+    } while (0)
+#define ASSERT_EQ(a, b) ASSERT((a) == (b))
+
+static std::mt19937_64 rng(0x5EED);
+// a canonical value below 2^380 < p (the crate samples with from_u768, src/fp.rs:218-253; any canonical value serves the laws)
+static Fp fp_rand() {
+    Fp a;
+    for (auto &l : a.v) l = rng();
+    a.v[5] &= (1ULL << 60) - 1;
+    return a;
+}
+static Fp2 fp2_rand() { return Fp2::new_(fp_rand(), fp_rand()); }
+static Fp6 fp6_rand() { return Fp6::new_(fp2_rand(), fp2_rand(), fp2_rand()); }
+static Fp12 fp12_rand() { return Fp12::new_(fp6_rand(), fp6_rand()); }
+template <class T> T rnd();
+template <> Fp rnd<Fp>() { return fp_rand(); }
+template <> Fp2 rnd<Fp2>() { return fp2_rand(); }
+template <> Fp6 rnd<Fp6>() { return fp6_rand(); }
+template <> Fp12 rnd<Fp12>() { return fp12_rand(); }
+
+#include "_kats.inc"  // KAT_* constants generated from tests/golden
+
+// test_equality / test_inequality
+template <class T> static void test_equality() {
+    for (int i = 0; i < 10; ++i) {
+        T a = rnd<T>(), b = a;
+        ASSERT_EQ(a, b);
+        T c = rnd<T>();
+        ASSERT(a != c);
+    }
+}
+
+// test_addition_subtraction
+template <class T> static void test_addition_subtraction() {
+    for (int i = 0; i < 10; ++i) {
+        T a = rnd<T>(), b = rnd<T>(), c = rnd<T>();
+        ASSERT_EQ(a + b, b + a);              // commutative
+        ASSERT_EQ(a + (b + c), (a + b) + c);  // associative
+        ASSERT_EQ(a + T::zero(), a);          // additive identity
+        ASSERT_EQ(a - T::zero(), a);
+        ASSERT_EQ(T::zero() - a, -a);
+        ASSERT_EQ(a - b, a + (-b));
+        ASSERT_EQ(a - b, a + (b * -T::one()));
+        ASSERT_EQ(-a, T::zero() - a);
+        ASSERT_EQ(-a, a * -T::one());
+    }
+}
+
+// test_multiplication
+template <class T> static void test_multiplication() {
+    for (int i = 0; i < 10; ++i) {
+        T a = rnd<T>(), b = rnd<T>(), c = rnd<T>();
+        ASSERT_EQ(a * b, b * a);
+        ASSERT_EQ(a * (b * c), (a * b) * c);
+        ASSERT_EQ(a * (b + c), a * b + a * c);
+    }
+}
+
+// test_add_equality: multiplication by small Fp scalars equals repeated addition
+template <class T> static void test_add_equality() {
+    for (int i = 0; i < 10; ++i) {
+        T a = rnd<T>();
+        ASSERT_EQ(a * Fp::from(0), T::zero());
+        ASSERT_EQ(a * T::zero(), T::zero());
+        ASSERT_EQ(a * T::one(), a);
+        ASSERT_EQ(a * Fp::from(1), a);
+        ASSERT_EQ(a * Fp::from(2), a + a);
+        ASSERT_EQ(a * Fp::from(3), a + a + a);
+        ASSERT_EQ(a * Fp::from(4), a + a + a + a);
+    }
+}
+
+// test_square_equality
+template <class T> static void test_square_equality() {
+    for (int i = 0; i < 10; ++i) {
+        T a = rnd<T>();
+        ASSERT_EQ(a.square(), a * a);
+    }
+}
+
+// test_pow_equality (Fp, Fp2, Fp12 have pow_vartime)
+template <class T> static void test_pow_equality() {
+    for (int i = 0; i < 10; ++i) {
+        T a = rnd<T>();
+        ASSERT_EQ(a.pow_vartime({1, 0, 0, 0, 0, 0}), a);
+        ASSERT_EQ(a.pow_vartime({2, 0, 0, 0, 0, 0}), a.square());
+        ASSERT_EQ(a.pow_vartime({3, 0, 0, 0, 0, 0}), a.square() * a);
+        ASSERT_EQ(a.pow_vartime({4, 0, 0, 0, 0, 0}), a.square().square());
+    }
+}
+
+// test_div, test_inversion; division by zero panics in the crate (unwrap on None)
+template <class T> static void test_div() {
+    for (int i = 0; i < 10; ++i) {
+        T a = rnd<T>();
+        ASSERT_EQ(a / T::one(), a);
+        ASSERT_EQ(a / a, T::one());
+        ASSERT_EQ(T::zero() / a, T::zero());
+        T b = rnd<T>(), c = rnd<T>();
+        a = rnd<T>();
+        ASSERT_EQ((a + b) / c, a / c + b / c);
+        a = rnd<T>();
+        b = rnd<T>();
+        ASSERT_EQ(a / b, a * *b.invert());
+        ASSERT_EQ(a * *a.invert(), T::one());
+        ASSERT_EQ(*a.invert()->invert(), a);
+    }
+    ASSERT(!T::zero().invert().has_value());
+    bool panicked = false;
+    try {
+        (void)(T::one() / T::zero());
+    } catch (const Panic &) {
+        panicked = true;
+    }
+    ASSERT(panicked);
+}
+
+template <class T> static void field_suite() {
+    test_equality<T>();
+    test_addition_subtraction<T>();
+    test_multiplication<T>();
+    test_add_equality<T>();
+    test_square_equality<T>();
+    test_div<T>();
+}
+
+// src/fp.rs:577-588
+static void test_fp_sqrt() {
+    Fp sqr1 = *Fp::from_raw_unchecked({KAT_SQRT_INPUT, 0, 0, 0, 0, 0}).sqrt();
+    ASSERT_EQ(sqr1.debug(), std::string("0x") + KAT_SQRT_HEX);
+    ASSERT(!Fp::from_raw_unchecked({KAT_SQRT_NON_RESIDUE, 0, 0, 0, 0, 0}).sqrt().has_value());
+}
+
+// Fp::from_bytes / to_bytes (src/fp.rs:165-207): round trip, and Err(()) for a non-canonical encoding
+static void test_fp_bytes() {
+    for (int i = 0; i < 10; ++i) {
+        Fp a = fp_rand();
+        ASSERT_EQ(*Fp::from_bytes(a.to_bytes()), a);
+    }
+    std::array<uint8_t, 48> ff;
+    ff.fill(0xff);
+    ASSERT(!Fp::from_bytes(ff).has_value());
+    ASSERT_EQ(Fp::one().to_bytes()[47], 1);
+}
+
+// src/fp6.rs:562-757 and src/fp12.rs:414-799: the fixed-operand identities of test_arithmetic
+template <class T> static void test_arithmetic(const T &a, const T &b, const T &c) {
+    ASSERT_EQ(a.square(), a * a);
+    ASSERT_EQ(b.square(), b * b);
+    ASSERT_EQ(c.square(), c * c);
+    ASSERT_EQ((a + b) * c.square(), (c * c * a) + (c * c * b));
+    ASSERT_EQ(*a.invert() * *b.invert(), *(a * b).invert());
+    ASSERT_EQ(*a.invert() * a, T::one());
+    // frobenius_map has order 6 on Fp6 and 12 on Fp12 (src/fp6.rs:748-757, src/fp12.rs:781-799)
+    ASSERT(a != a.frobenius_map());
+    T f = a;
+    for (size_t k = 0; k < sizeof(T) / sizeof(Fp); ++k) f = f.frobenius_map();
+    ASSERT_EQ(f, a);
+}
+
+static void test_tower_specials() {
+    for (int i = 0; i < 5; ++i) {
+        Fp2 a = fp2_rand();
+        ASSERT_EQ(a.mul_by_nonresidue(), a * Fp2::new_(Fp::one(), Fp::one()));  // x (1+u), src/fp2.rs:161-168
+        ASSERT_EQ(a.frobenius_map(), a.conjugate());
+        ASSERT_EQ(a.conjugate().conjugate(), a);
+        Fp6 s = fp6_rand();
+        Fp2 c0 = fp2_rand(), c1 = fp2_rand(), c4 = fp2_rand();
+        ASSERT_EQ(s.mul_by_1(c1), s * Fp6::new_(Fp2::zero(), c1, Fp2::zero()));       // src/fp6.rs:102-108
+        ASSERT_EQ(s.mul_by_01(c0, c1), s * Fp6::new_(c0, c1, Fp2::zero()));           // src/fp6.rs:110-125
+        ASSERT_EQ(s.mul_by_nonresidue(), s * Fp6::new_(Fp2::zero(), Fp2::one(), Fp2::zero()));  // x v
+        Fp12 f = fp12_rand();
+        ASSERT_EQ(f.mul_by_014(c0, c1, c4),                                           // src/fp12.rs:99-111
+                  f * Fp12::new_(Fp6::new_(c0, c1, Fp2::zero()), Fp6::new_(Fp2::zero(), c4, Fp2::zero())));
+        ASSERT_EQ(f.conjugate().conjugate(), f);
+        // frobenius_map is the TRUE a -> a^p here (12 applications = identity, and it is multiplicative)
+        Fp12 g = f;
+        for (int k = 0; k < 12; ++k) g = g.frobenius_map();
+        ASSERT_EQ(g, f);
+        Fp12 h = fp12_rand();
+        ASSERT_EQ((f * h).frobenius_map(), f.frobenius_map() * h.frobenius_map());
+        ASSERT_EQ(f.frobenius_map(), f.pow_vartime(KAT_P));
+        Fp6 t = s;
+        for (int k = 0; k < 6; ++k) t = t.frobenius_map();
+        ASSERT_EQ(t, s);
+    }
+    // From<Fp> replicates the value into every coefficient (src/fp2.rs:32-36)
+    Fp x = fp_rand();
+    ASSERT_EQ(Fp2::from(x).c1, x);
+    ASSERT_EQ(Fp12::from(x).c1.c2.c1, x);
+    ASSERT(Fp12::from(Fp2::from(x)).c1.is_zero());
+}
+
+// src/g1.rs:215-341
+static void test_g1() {
+    ASSERT(G1Affine::generator().is_valid().is_ok());
+    ASSERT(G1Affine::identity().is_valid().is_ok());
+    ASSERT(G1Affine::identity().is_identity());
+    for (size_t i = 0; i < sizeof(KAT_G1_DOUBLE) / sizeof(KAT_G1_DOUBLE[0]); ++i) {
+        G1Affine a = G1Affine::new_(KAT_G1_DOUBLE[i][0], KAT_G1_DOUBLE[i][1], false);
+        G1Affine a_double = G1Affine::new_(KAT_G1_DOUBLE[i][2], KAT_G1_DOUBLE[i][3], false);
+        ASSERT_EQ(a.double_(), a_double);
+        ASSERT_EQ(a * fr_from(2), a_double);
+    }
+    G1Affine g = G1Affine::generator();
+    ASSERT_EQ((g * fr_from(5)) * fr_from(7), g * fr_from(35));
+    ASSERT_EQ(-(g * fr_from(3)), (-g) * fr_from(3));
+    ASSERT((g * KAT_R).is_identity());  // r * G = identity
+    G1Affine off = G1Affine::new_(g.x, g.x, false);
+    ASSERT_EQ(off.is_valid().err, std::string("Point is not on curve"));
+    ASSERT(!off.is_on_curve());
+}
+
+// src/g2.rs:264-443
+static void test_g2() {
+    G2Affine g = G2Affine::generator();
+    ASSERT(g.is_valid().is_ok());
+    ASSERT(G2Affine::identity().is_valid().is_ok());
+    G2Affine g_double = G2Affine::new_(KAT_G2_DOUBLE[0], KAT_G2_DOUBLE[1], false);   // test_doubling
+    ASSERT_EQ(g.double_(), g_double);
+    for (int i = 0; i < 5; ++i) {                                                       // test_scalar_multiplication
+        uint64_t r = rng() % 100, s = rng() % 100;
+        ASSERT_EQ((g * fr_from(r)) * fr_from(s), g * fr_from(r * s));
+    }
+    ASSERT((g * fr_from(0)).is_identity());
+    ASSERT((g * KAT_R).is_identity());
+    G2Affine a = G2Affine::new_(KAT_G2_NOT_TORSION_FREE[0], KAT_G2_NOT_TORSION_FREE[1], false);  // test_torsion_free
+    ASSERT(!a.is_torsion_free());   // (the crate's vector is a Montgomery-form point of its lineage: as canonical limbs it is
+    ASSERT(a.is_valid().is_err());  //  not even on the curve, so is_valid reports the first failing check)
+    ASSERT_EQ(a.is_valid().err, std::string("Point is not on curve"));
+    ASSERT(g.is_torsion_free());
+}
+
+// the module the crate leaves empty (src/pairings.rs): SURVEY 8d config 1
+static void test_pairings() {
+    using namespace pairings;
+    G1Affine p = G1Affine::generator();
+    G2Affine q = G2Affine::generator();
+    Gt e = pairing(p, q);
+    ASSERT_EQ(e, KAT_E_G1_G2);                                    // published Gt generator
+    ASSERT_EQ(final_exponentiation(miller_loop(p, q)), e);
+    ASSERT_EQ(e.pow_vartime({KAT_R[0], KAT_R[1], KAT_R[2], KAT_R[3], 0, 0}), Gt::one());  // e^r = 1
+    ASSERT(e != Gt::one());
+    const uint64_t ab[][2] = {{2, 3}, {5, 8}, {7, 7}, {0x1234567, 0x89abcd}};
+    for (auto &s : ab) {                                                     // e(aP, bQ) = e(P, Q)^(ab)
+        Gt lhs = pairing(p * fr_from(s[0]), q * fr_from(s[1]));
+        ASSERT_EQ(lhs, e.pow_vartime({s[0] * s[1], 0, 0, 0, 0, 0}));
+        ASSERT_EQ(pairing(p * fr_from(s[0] * s[1]), q), lhs);
+    }
+    ASSERT_EQ(pairing(G1Affine::identity(), q), Gt::one());
+    ASSERT_EQ(pairing(p, G2Affine::identity()), Gt::one());
+    // multi_miller_loop over k pairs == product of the single Miller loops, bit for bit
+    G1Affine p2 = p * fr_from(11), p3 = p * fr_from(13);
+    G2Affine q2 = q * fr_from(17), q3 = q * fr_from(19);
+    Fp12 mm = multi_miller_loop({{p, q}, {p2, q2}, {p3, q3}});
+    ASSERT_EQ(mm, miller_loop(p, q) * miller_loop(p2, q2) * miller_loop(p3, q3));
+    // e(P,Q) e(-P,Q) = 1 as a 2-pair product check with a shared final exponentiation
+    auto chk = multi_pairing_batch({p, -p, p, p2}, {q, q, q, q2}, 2);
+    ASSERT_EQ(chk.first[0], Gt::one());
+    ASSERT(chk.second[0] && !chk.second[1]);
+    ASSERT_EQ(chk.first[1], pairing(p, q) * pairing(p2, q2));
+    ASSERT_EQ(multi_miller_product({p, p2, p3}, {q, q2, q3}), final_exponentiation(mm));
+    // batch == singles
+    auto batch = pairing_batch({p, p2, p3}, {q3, q2, q});
+    ASSERT_EQ(batch[0], pairing(p, q3));
+    ASSERT_EQ(batch[2], pairing(p3, q));
+    // a limb vector >= p is rejected, never silently reduced
+    G1Affine bad = p;
+    for (auto &l : bad.x.v) l = ~0ULL;
+    bool rejected = false;
+    try {
+        (void)pairing(bad, q);
+    } catch (const Error &err) {
+        rejected = err.code == ZKP_ERR_NONCANONICAL;
+    }
+    ASSERT(rejected);
+}
+
+int main() {
+    try {
+        field_suite<Fp>();
+        field_suite<Fp2>();
+        field_suite<Fp6>();
+        field_suite<Fp12>();
+        test_pow_equality<Fp>();
+        test_pow_equality<Fp2>();
+        test_pow_equality<Fp12>();
+        test_fp_sqrt();
+        test_fp_bytes();
+        test_arithmetic<Fp6>(KAT_FP6_A, KAT_FP6_B, KAT_FP6_C);
+        test_arithmetic<Fp12>(KAT_FP12_A, KAT_FP12_B, KAT_FP12_C);
+        test_tower_specials();
+        test_g1();
+        test_g2();
+        test_pairings();
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "exception: %s\n", e.what());
+        return 2;
+    }
+    std::printf("ok %d checks\n", g_checks);
+    return 0;
+}
