@@ -220,7 +220,7 @@ ZKP_HD void pairing_front(Fp12 &f, bool &bad, int mode, const uint64_t *g1, cons
     }
 }
 // the whole check in one call (dev simulation and small helpers; the GPU path splits the final
-// exponentiation over three launches, pairing_kernel.cu)
+// exponentiation over 13 launches, pairing_kernel.cu)
 template <int K>
 ZKP_HD uint8_t pairing_one(int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
                            int k, const uint64_t *in12, uint64_t *out, uint8_t *is_one, bool live = true) {

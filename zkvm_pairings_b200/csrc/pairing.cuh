@@ -161,52 +161,178 @@ ZKP_NOINLINE void cyclotomic_exp(Fp12 &r, const Fp12 &f) {
     fp12_conj(r, t);
 }
 
-// SURVEY 9.2, split around the single Fp inversion of the easy part (f^-1): fe_prepare leaves the
-// cofactors and the norm n, fe_finish continues from ninv = 1/n.  The pairing kernels run the two
-// halves as separate launches with a batched inversion kernel in between (Montgomery's trick across
-// pairings: ~41 Fp products per inverse instead of a 609-product Fermat ladder per lane).
-// f must be non-zero (a Miller-loop output always is); zero maps to zero.
+// ------------------------------------------------------------------ compressed cyclotomic squarings
+//
+// In the w-power basis f = A + B w + C w^2 over Fp4 = Fp2[s]/(s^2 - xi), s = w^3, with
+//   A = z0 + z1 s = (c0.c0, c1.c1),  B = z2 + z3 s = (c1.c0, c0.c2),  C = z4 + z5 s = (c0.c1, c1.c2),
+// the Granger-Scott squaring reads A' = 3A^2 - 2conj(A), B' = 3 s C^2 + 2conj(B), C' = 3B^2 - 2conj(C):
+// B and C evolve WITHOUT A (Karabina's compressed form).  A long run of squarings therefore costs 6 Fp2
+// squarings each instead of 9, and A is recovered at the end from the subgroup relations
+//   z2 != 0:  z1 = (xi z5^2 + 3 z4^2 - 2 z3) / (4 z2)         z2 == 0:  z1 = 2 z4 z5 / z3
+//   z0 = xi (2 z1^2 + z2 z5 - 3 z3 z4) + 1
+// at the price of one Fp2 inversion.  f^|x| (|x| = 2^63+2^62+2^60+2^57+2^48+2^16) = the product of six
+// powers f^(2^k): the chain runs compressed up to 2^57 with snapshots at 2^16, 2^48, 2^57, the three
+// denominators are inverted together (Montgomery's trick) through ONE Fp inversion -- which the GPU path
+// batches across pairings in a separate launch, like the inversion of the easy part -- and the last six
+// squarings run uncompressed.  57 x 6 + 6 x 9 = 396 Fp2 squarings instead of 63 x 9 = 567 per f^|x|.
+// Results are the same field elements as cyclotomic_exp (tools/karabina_proto.py checks the formulas
+// against the oracle); the elements must lie in the cyclotomic subgroup, which everything after the easy
+// part does.  z2 = z3 = 0 only happens for f = 1 (the denominator is replaced by 1, the formulas give 1).
+static_assert(ZKP_BLS_X == ((1ull << 63) | (1ull << 62) | (1ull << 60) | (1ull << 57) | (1ull << 48) | (1ull << 16)),
+              "the compressed chain hard-codes the bits of |x|");
+#define ZKP_CEXP_RUN 57   // squarings done in compressed form (up to the third set bit of |x|)
+
+struct CExp {            // one f^|x| between its two halves
+    Fp2 s[3][4];         // (z2, z3, z4, z5) of f^(2^16), f^(2^48), f^(2^57)
+    Fp2 p1, p2;          // d1, d1 d2 (prefix products of the three denominators)
+    Fp2 t;               // d1 d2 d3: the Fp2 whose norm goes to the (batched) Fp inversion
+};
+// z = (z2, z3, z4, z5) <- the same four coefficients of the square; 6 Fp2 squarings
+ZKP_NOINLINE void cyc_sqr_compressed(Fp2 *z) {
+    Fp2 t0, t1, t2, t3;
+    fp4_square(t0, t1, z[0], z[1]);
+    fp4_square(t2, t3, z[2], z[3]);
+    Fp2 n4 = cyc_minus(t0, z[2]);
+    Fp2 n5 = cyc_plus(t1, z[3]);
+    t0 = fp2_mul_nr(t3);
+    z[0] = cyc_plus(t0, z[0]);
+    z[1] = cyc_minus(t2, z[1]);
+    z[2] = n4;
+    z[3] = n5;
+}
+// the denominator of the z1 formula: 4 z2, or z3 when z2 = 0, or 1 when both vanish (f = 1)
+ZKP_HD Fp2 cexp_den(const Fp2 *z) {
+    Fp2 d = fp2_select(fp2_is_zero(z[0]), z[1], fp2_dbl(fp2_dbl(z[0])));
+    return fp2_select(fp2_is_zero(d), fp2_one(), d);
+}
+// first half: the compressed run and the product of the denominators; returns the norm to invert
+ZKP_NOINLINE Fp cexp_begin(CExp &c, const Fp12 &f) {
+    Fp2 z[4] = {f.c1.c0, f.c0.c2, f.c0.c1, f.c1.c2};
+    int k = 0;
+#pragma unroll 1
+    for (int i = 1; i <= ZKP_CEXP_RUN; i++) {
+        cyc_sqr_compressed(z);
+        if ((ZKP_BLS_X >> i) & 1) {
+            for (int j = 0; j < 4; j++) c.s[k][j] = z[j];
+            k++;
+        }
+    }
+    c.p1 = cexp_den(c.s[0]);
+    c.p2 = fp2_mul(c.p1, cexp_den(c.s[1]));
+    c.t = fp2_mul(c.p2, cexp_den(c.s[2]));
+    return fp2_norm(c.t);
+}
+// g <- the full element of a snapshot z = (z2..z5); dinv = 1 / cexp_den(z)
+ZKP_NOINLINE void cexp_decompress(Fp12 &g, const Fp2 *z, const Fp2 &dinv) {
+    Fp2 s4 = fp2_sqr(z[2]);
+    Fp2 num_a = fp2_sub(fp2_add(fp2_mul_nr(fp2_sqr(z[3])), fp2_add(fp2_dbl(s4), s4)), fp2_dbl(z[1]));
+    Fp2 num_b = fp2_dbl(fp2_mul(z[2], z[3]));
+    Fp2 z1 = fp2_mul(fp2_select(fp2_is_zero(z[0]), num_b, num_a), dinv);
+    Fp2 m = fp2_mul(z[1], z[2]);
+    Fp2 t = fp2_add(fp2_dbl(fp2_sqr(z1)), fp2_mul(z[0], z[3]));   // z2 z5 vanishes by itself when z2 = 0
+    t = fp2_sub(t, fp2_add(fp2_dbl(m), m));
+    g.c0.c0 = fp2_add(fp2_mul_nr(t), fp2_one());
+    g.c1.c1 = z1;
+    g.c1.c0 = z[0];
+    g.c0.c2 = z[1];
+    g.c0.c1 = z[2];
+    g.c1.c2 = z[3];
+}
+// second half, from ninv = 1 / norm(c.t): r = conj(f^|x|) = f^x
+ZKP_NOINLINE void cexp_end(Fp12 &r, const CExp &c, const Fp &ninv) {
+    Fp2 inv = fp2_inv_finish(c.t, ninv);              // 1 / (d1 d2 d3)
+    Fp2 i3 = fp2_mul(inv, c.p2);
+    inv = fp2_mul(inv, cexp_den(c.s[2]));             // 1 / (d1 d2)
+    Fp2 i2 = fp2_mul(inv, c.p1);
+    Fp2 i1 = fp2_mul(inv, cexp_den(c.s[1]));
+    Fp12 a, g;
+    cexp_decompress(a, c.s[0], i1);
+    cexp_decompress(g, c.s[1], i2);
+    fp12_mul(a, a, g);
+    cexp_decompress(g, c.s[2], i3);
+    fp12_mul(a, a, g);
+#pragma unroll 1
+    for (int b = ZKP_CEXP_RUN + 1; b <= 63; b++) {
+        fp12_cyclotomic_sqr(g, g);
+        if ((ZKP_BLS_X >> b) & 1) fp12_mul(a, a, g);
+    }
+    fp12_conj(r, a);
+}
+
+// SURVEY 9.2 as a pipeline of SIX stages separated by Fp inversions: the one of the easy part (f^-1,
+// fe_prepare leaves the cofactors and the norm) and one per f^x of the hard part (the decompression
+// above).  The GPU path runs every stage as a launch with a batched inversion kernel in between
+// (Montgomery's trick across pairings: ~41 Fp products per inverse instead of a 609-product Fermat ladder
+// per lane, pairing_kernel.cu); final_exponentiation() below chains the same stages with in-lane
+// inversions (dev simulation, small helpers).  With m = the easy part's output the stages compute
+//   a = m^x, b = a^2, c = m^-2 a, d = c^x, e = d^x, g = e^x b, h = g^x
+//   result = conj(c) m . frob3(d m) . frob2(a e) . frob(g conj(m)) . h
+// -- the zkcrypto-lineage addition chain of SURVEY 9.2 with its products reassociated so that at most
+// four Fp12 (m, a, b, acc) are live across a stage boundary.
+// f must be non-zero (a Miller-loop output always is); zero maps to zero (acc carries the factor m = 0).
 struct FeState {
     Fp6 c;   // cofactors of the Fp6 inverse
     Fp2 t;   // the Fp2 whose norm is inverted
 };
+struct FeWork {
+    Fp12 m, a, b, acc;
+    CExp c;
+};
+#define ZKP_FE_STAGES 6
 ZKP_HD Fp fe_prepare(FeState &s, const Fp12 &f) { return fp12_inv_prepare(s.c, s.t, f); }
-ZKP_HD void fe_finish(Fp12 &r, const Fp12 &f, const FeState &s, const Fp &ninv) {
-    Fp12 t0, t1, t2, t3, t4, t5, t6;
-    fp12_conj(t0, f);                 // f^(p^6)
-    fp12_inv_finish(t1, f, s.c, s.t, ninv);
-    fp12_mul(t2, t0, t1);             // f^(p^6-1)
-    t1 = t2;
-    fp12_frobenius(t2, t2, 2);
-    fp12_mul(t2, t2, t1);             // easy part done
-    fp12_cyclotomic_sqr(t1, t2);
-    fp12_conj(t1, t1);
-    cyclotomic_exp(t3, t2);
-    fp12_cyclotomic_sqr(t4, t3);
-    fp12_mul(t5, t1, t3);
-    cyclotomic_exp(t1, t5);
-    cyclotomic_exp(t0, t1);
-    cyclotomic_exp(t6, t0);
-    fp12_mul(t6, t6, t4);
-    cyclotomic_exp(t4, t6);
-    fp12_conj(t5, t5);
-    fp12_mul(t5, t5, t2);
-    fp12_mul(t4, t4, t5);
-    fp12_conj(t5, t2);
-    fp12_mul(t1, t1, t2);
-    fp12_frobenius(t1, t1, 3);
-    fp12_mul(t6, t6, t5);
-    fp12_frobenius(t6, t6, 1);
-    fp12_mul(t3, t3, t0);
-    fp12_frobenius(t3, t3, 2);
-    fp12_mul(t3, t3, t1);
-    fp12_mul(t3, t3, t6);
-    fp12_mul(r, t3, t4);
+// stage 0 consumes (f, s) and 1/norm of fe_prepare; stage k > 0 consumes w and 1/norm of stage k-1;
+// every stage but the last returns the next norm to invert, the last writes *result.
+ZKP_HD Fp fe_stage(int stage, FeWork &w, const Fp12 *f, const FeState *s, const Fp &ninv, Fp12 *result) {
+    Fp12 x, t;
+    switch (stage) {
+        case 0:
+            fp12_conj(x, *f);
+            fp12_inv_finish(t, *f, s->c, s->t, ninv);
+            fp12_mul(x, x, t);                 // f^(p^6 - 1)
+            fp12_frobenius(t, x, 2);
+            fp12_mul(w.m, t, x);               // easy part done
+            return cexp_begin(w.c, w.m);
+        case 1:
+            cexp_end(w.a, w.c, ninv);
+            fp12_cyclotomic_sqr(w.b, w.a);
+            fp12_cyclotomic_sqr(t, w.m);
+            fp12_conj(t, t);                   // m^-2
+            fp12_mul(x, t, w.a);               // c
+            fp12_conj(t, x);
+            fp12_mul(w.acc, t, w.m);
+            return cexp_begin(w.c, x);
+        case 2:
+            cexp_end(x, w.c, ninv);            // d
+            fp12_mul(t, x, w.m);
+            fp12_frobenius(t, t, 3);
+            fp12_mul(w.acc, w.acc, t);
+            return cexp_begin(w.c, x);
+        case 3:
+            cexp_end(x, w.c, ninv);            // e
+            fp12_mul(t, w.a, x);
+            fp12_frobenius(t, t, 2);
+            fp12_mul(w.acc, w.acc, t);
+            return cexp_begin(w.c, x);
+        case 4:
+            cexp_end(x, w.c, ninv);
+            fp12_mul(x, x, w.b);               // g
+            fp12_conj(t, w.m);
+            fp12_mul(t, x, t);
+            fp12_frobenius(t, t, 1);
+            fp12_mul(w.acc, w.acc, t);
+            return cexp_begin(w.c, x);
+        default:
+            cexp_end(x, w.c, ninv);            // h
+            fp12_mul(*result, w.acc, x);
+            return fp_zero();
+    }
 }
 ZKP_HD void final_exponentiation(Fp12 &r, const Fp12 &f) {
     FeState s;
+    FeWork w;
     Fp n = fe_prepare(s, f);
-    fe_finish(r, f, s, fp_inv(n));
+    Fp12 in = f;
+    for (int stage = 0; stage < ZKP_FE_STAGES; stage++) n = fe_stage(stage, w, &in, &s, fp_inv(n), &r);
 }
 
 // Montgomery's trick over a run of values held by ONE thread: v[i] <- 1/v[i] for i < cnt with a

@@ -23,16 +23,57 @@ using namespace zkp;
 
 // ------------------------------------------------------------------ final-exponentiation scratch
 //
-// The final exponentiation is three launches: k_pairing (Miller loop and/or load, then fe_prepare)
-// -> k_fe_batch_inv -> k_fe_finish.  Between them each lane parks its half of f (6 Fp), of the
-// inverse cofactors (3 Fp) and of t (1 Fp) in `lanes`, and the pair's norm in `norm` -- internal
-// Montgomery limbs, never seen by the caller.
-#define ZKP_FE_LANE_FP 10
+// The final exponentiation is 13 launches: k_pairing (Miller loop and/or load, then fe_prepare), then for
+// each of the six stages of pairing.cuh's fe_stage a k_fe_batch_inv (the stage's one Fp inversion,
+// batched across pairings) followed by k_fe_stage.  Between launches each lane parks its half of the
+// live values in `lanes` and the pair's norm in `norm` -- internal Montgomery limbs, never seen by the
+// caller.  Layout: slot-major, lanes[slot][2 n] Fp, so that the 32 lanes of a warp touch one contiguous
+// 1536-byte run per slot (coalesced 128-bit loads/stores).  Slots (Fp per lane):
+//   0..5 m   6..11 a   12..17 b   18..23 acc   24..35 the three snapshots   36 p1   37 p2   38 t
+// stage 0's inputs reuse slots that are first written by stage 1: f in 6..11, the FeState in 12..15.
+// A stage moves only what it reads / changes: ~25 KB per pairing over the whole pipeline, 0.6 % of the
+// step at HBM speed.
+#define ZKP_FE_LANE_FP 39
+#define ZKP_SLOT_M 0
+#define ZKP_SLOT_A 6
+#define ZKP_SLOT_B 12
+#define ZKP_SLOT_ACC 18
+#define ZKP_SLOT_CEXP 24
+#define ZKP_SLOT_F ZKP_SLOT_A
+#define ZKP_SLOT_FES ZKP_SLOT_B
 struct FeScratch {
-    Fp *lanes;   // [2 * n][ZKP_FE_LANE_FP]
+    Fp *lanes;   // [ZKP_FE_LANE_FP][2 * n]
     Fp *norm;    // [n], replaced by its inverse in place
+    size_t n2;   // 2 * n
 };
 extern "C" size_t zkp_fe_scratch_bytes(size_t n) { return n * (2 * ZKP_FE_LANE_FP + 1) * sizeof(Fp); }
+
+ZKP_HD void park_fp12(const FeScratch &fs, size_t lane, int slot, const Fp12 &f) {
+    const Fp2 *c = &f.c0.c0;
+#pragma unroll
+    for (int j = 0; j < 6; j++) fs.lanes[(size_t)(slot + j) * fs.n2 + lane] = c[j].c;
+}
+ZKP_HD void fetch_fp12(const FeScratch &fs, size_t lane, int slot, Fp12 &f) {
+    Fp2 *c = &f.c0.c0;
+#pragma unroll
+    for (int j = 0; j < 6; j++) c[j].c = fs.lanes[(size_t)(slot + j) * fs.n2 + lane];
+}
+ZKP_HD void park_cexp(const FeScratch &fs, size_t lane, const CExp &c) {
+    const Fp2 *z = &c.s[0][0];
+#pragma unroll
+    for (int j = 0; j < 12; j++) fs.lanes[(size_t)(ZKP_SLOT_CEXP + j) * fs.n2 + lane] = z[j].c;
+    fs.lanes[(size_t)(ZKP_SLOT_CEXP + 12) * fs.n2 + lane] = c.p1.c;
+    fs.lanes[(size_t)(ZKP_SLOT_CEXP + 13) * fs.n2 + lane] = c.p2.c;
+    fs.lanes[(size_t)(ZKP_SLOT_CEXP + 14) * fs.n2 + lane] = c.t.c;
+}
+ZKP_HD void fetch_cexp(const FeScratch &fs, size_t lane, CExp &c) {
+    Fp2 *z = &c.s[0][0];
+#pragma unroll
+    for (int j = 0; j < 12; j++) z[j].c = fs.lanes[(size_t)(ZKP_SLOT_CEXP + j) * fs.n2 + lane];
+    c.p1.c = fs.lanes[(size_t)(ZKP_SLOT_CEXP + 12) * fs.n2 + lane];
+    c.p2.c = fs.lanes[(size_t)(ZKP_SLOT_CEXP + 13) * fs.n2 + lane];
+    c.t.c = fs.lanes[(size_t)(ZKP_SLOT_CEXP + 14) * fs.n2 + lane];
+}
 
 // mode: bit0 Miller loop, bit1 first half of the final exponentiation.  One lane pair per check of
 // k (<= K) pairs.  Without bit1 the Miller output is stored canonically to `out`.
@@ -54,11 +95,12 @@ k_pairing(int mode, const uint64_t *__restrict__ g1, const uint8_t *__restrict__
         FeState s;
         Fp nrm = fe_prepare(s, f);
         if (live) {
-            Fp *L = fs.lanes + (2 * i + lane_par()) * ZKP_FE_LANE_FP;
-            const Fp2 *c = &f.c0.c0;
-#pragma unroll
-            for (int j = 0; j < 6; j++) L[j] = c[j].c;
-            L[6] = s.c.c0.c; L[7] = s.c.c1.c; L[8] = s.c.c2.c; L[9] = s.t.c;
+            size_t lane = 2 * i + lane_par();
+            park_fp12(fs, lane, ZKP_SLOT_F, f);
+            fs.lanes[(size_t)(ZKP_SLOT_FES + 0) * fs.n2 + lane] = s.c.c0.c;
+            fs.lanes[(size_t)(ZKP_SLOT_FES + 1) * fs.n2 + lane] = s.c.c1.c;
+            fs.lanes[(size_t)(ZKP_SLOT_FES + 2) * fs.n2 + lane] = s.c.c2.c;
+            fs.lanes[(size_t)(ZKP_SLOT_FES + 3) * fs.n2 + lane] = s.t.c;
             if (lane_par() == 0) fs.norm[i] = nrm;
         }
     } else {
@@ -81,23 +123,47 @@ __global__ void __launch_bounds__(128) k_fe_batch_inv(Fp *norm, size_t n) {
     fp_batch_inv(norm + lo, pre, cnt);
 }
 
-// second half of the final exponentiation
+// one stage of the final exponentiation (pairing.cuh fe_stage): consumes the inverse the preceding
+// k_fe_batch_inv left in norm[i], leaves the next norm there; the last stage stores the result
 __global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS_FE)
-k_fe_finish(FeScratch fs, uint64_t *__restrict__ out, uint8_t *__restrict__ is_one, size_t n) {
+k_fe_stage(int stage, FeScratch fs, uint64_t *__restrict__ out, uint8_t *__restrict__ is_one, size_t n) {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     bool live = i < n;
     if (!live) i = n - 1;
-    const Fp *L = fs.lanes + (2 * i + lane_par()) * ZKP_FE_LANE_FP;
+    size_t lane = 2 * i + lane_par();
+    FeWork w;
     Fp12 f;
     FeState s;
-    Fp2 *c = &f.c0.c0;
-#pragma unroll
-    for (int j = 0; j < 6; j++) c[j].c = L[j];
-    s.c.c0.c = L[6]; s.c.c1.c = L[7]; s.c.c2.c = L[8]; s.t.c = L[9];
+    if (stage == 0) {
+        fetch_fp12(fs, lane, ZKP_SLOT_F, f);
+        s.c.c0.c = fs.lanes[(size_t)(ZKP_SLOT_FES + 0) * fs.n2 + lane];
+        s.c.c1.c = fs.lanes[(size_t)(ZKP_SLOT_FES + 1) * fs.n2 + lane];
+        s.c.c2.c = fs.lanes[(size_t)(ZKP_SLOT_FES + 2) * fs.n2 + lane];
+        s.t.c = fs.lanes[(size_t)(ZKP_SLOT_FES + 3) * fs.n2 + lane];
+    } else {
+        fetch_cexp(fs, lane, w.c);
+        if (stage != 1) fetch_fp12(fs, lane, ZKP_SLOT_ACC, w.acc);
+        if (stage == 1 || stage == 2 || stage == 4) fetch_fp12(fs, lane, ZKP_SLOT_M, w.m);
+        if (stage == 3) fetch_fp12(fs, lane, ZKP_SLOT_A, w.a);
+        if (stage == 4) fetch_fp12(fs, lane, ZKP_SLOT_B, w.b);
+    }
     Fp ninv = fs.norm[i];
-    fe_finish(f, f, s, ninv);
-    bool one = store_fp12(out + 72 * i, f, live);
-    if (is_one && live && lane_par() == 0) is_one[i] = one ? 1 : 0;
+    Fp nrm = fe_stage(stage, w, &f, &s, ninv, &f);
+    if (stage == ZKP_FE_STAGES - 1) {
+        bool one = store_fp12(out + 72 * i, f, live);
+        if (is_one && live && lane_par() == 0) is_one[i] = one ? 1 : 0;
+        return;
+    }
+    if (live) {
+        park_cexp(fs, lane, w.c);
+        if (stage == 0) park_fp12(fs, lane, ZKP_SLOT_M, w.m);
+        if (stage == 1) {
+            park_fp12(fs, lane, ZKP_SLOT_A, w.a);
+            park_fp12(fs, lane, ZKP_SLOT_B, w.b);
+        }
+        if (stage >= 1) park_fp12(fs, lane, ZKP_SLOT_ACC, w.acc);
+        if (lane_par() == 0) fs.norm[i] = nrm;
+    }
 }
 
 static int pair_capacity(int k) { return k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : 8; }
@@ -110,6 +176,7 @@ cudaError_t zkp_launch_k_pairing(int mode, const uint64_t *g1, const uint8_t *g1
     FeScratch fs;
     fs.lanes = (Fp *)scratch;
     fs.norm = fs.lanes ? fs.lanes + 2 * n * ZKP_FE_LANE_FP : nullptr;
+    fs.n2 = 2 * n;
     dim3 g((unsigned)((2 * n + ZKP_TPB - 1) / ZKP_TPB)), b(ZKP_TPB);
     switch (pair_capacity(k)) {
         case 1: k_pairing<1><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
@@ -120,9 +187,11 @@ cudaError_t zkp_launch_k_pairing(int mode, const uint64_t *g1, const uint8_t *g1
     *launches = 1;
     if (mode & ZKP_DO_FINAL_EXP) {
         size_t threads = (n + ZKP_INV_RUN - 1) / ZKP_INV_RUN;
-        k_fe_batch_inv<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(fs.norm, n);
-        k_fe_finish<<<g, b, 0, st>>>(fs, out, is_one, n);
-        *launches = 3;
+        for (int stage = 0; stage < ZKP_FE_STAGES; stage++) {
+            k_fe_batch_inv<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(fs.norm, n);
+            k_fe_stage<<<g, b, 0, st>>>(stage, fs, out, is_one, n);
+        }
+        *launches = 1 + 2 * ZKP_FE_STAGES;
     }
     return cudaGetLastError();
 }
