@@ -69,10 +69,18 @@ ZKP_NOINLINE void addition_step(G2P &r, const G2A &q, Fp2 *co) {
 // infinity) multiplies f by the line (1, 0, 0) = one instead -- by selects, not by a branch, so all
 // lanes of a warp stay on one path.
 ZKP_HD Fp2 fp2_select(bool c, const Fp2 &a, const Fp2 &b) { Fp2 r; r.c = fp_select(c, a.c, b.c); return r; }
-ZKP_HD void ell(Fp12 &f, const Fp2 *co, const G1A &p, bool skip) {
+// `first`: f is still one (the very first line of the loop), so the product is the line itself.
+ZKP_HD void ell(Fp12 &f, const Fp2 *co, const G1A &p, bool skip, bool first = false) {
     Fp2 a = fp2_select(skip, fp2_zero(), fp2_mul_fp(co[0], p.y));
     Fp2 b = fp2_select(skip, fp2_zero(), fp2_mul_fp(co[1], p.x));
-    fp12_mul_by_014(f, fp2_select(skip, fp2_one(), co[2]), b, a);
+    Fp2 c = fp2_select(skip, fp2_one(), co[2]);
+    if (first) {   // 1 * (c + b v + a v w)
+        f.c0.c0 = c;
+        f.c0.c1 = b;
+        f.c1.c1 = a;
+    } else {
+        fp12_mul_by_014(f, c, b, a);
+    }
 }
 
 // Bits of |x| >> 1 below its leading one (bit 62), MSB first: 62 iterations, additions where set.
@@ -108,11 +116,11 @@ ZKP_HD void miller_loop(Fp12 &f, const G1A *ps, const G2A *qs, const bool *skip,
         bool bit = b >= 0 && ((ZKP_X_HALF >> b) & 1);
         for (int j = 0; j < kv; j++) {
             doubling_step(rs[j], co);
-            ell(f, co, ps[j], skip[j]);
+            ell(f, co, ps[j], skip[j], step == 0 && j == 0);
         }
         for (int j = 0; j < kf; j++) {
             for (int c = 0; c < 3; c++) co[c] = line_tab_load(tab, j, step, c);
-            ell(f, co, ps[kv + j], skip[kv + j]);
+            ell(f, co, ps[kv + j], skip[kv + j], step == 0 && kv == 0 && j == 0);
         }
         step++;
         if (bit) {
@@ -173,8 +181,9 @@ ZKP_NOINLINE void cyclotomic_exp(Fp12 &r, const Fp12 &f) {
 // at the price of one Fp2 inversion.  f^|x| (|x| = 2^63+2^62+2^60+2^57+2^48+2^16) = the product of six
 // powers f^(2^k): the chain runs compressed up to 2^57 with snapshots at 2^16, 2^48, 2^57, the three
 // denominators are inverted together (Montgomery's trick) through ONE Fp inversion -- which the GPU path
-// batches across pairings in a separate launch, like the inversion of the easy part -- and the last six
-// squarings run uncompressed.  57 x 6 + 6 x 9 = 396 Fp2 squarings instead of 63 x 9 = 567 per f^|x|.
+// batches across pairings in a separate launch, like the inversion of the easy part -- and the top bits
+// (105 * 2^57) are finished uncompressed as (y^7)^15.  57 x 6 + 7 x 9 = 405 Fp2 squarings and 4 Fp12
+// products instead of 63 x 9 = 567 and 5 per f^|x|.
 // Results are the same field elements as cyclotomic_exp (tools/karabina_proto.py checks the formulas
 // against the oracle); the elements must lie in the cyclotomic subgroup, which everything after the easy
 // part does.  z2 = z3 = 0 only happens for f = 1 (the denominator is replaced by 1, the formulas give 1).
@@ -245,17 +254,25 @@ ZKP_NOINLINE void cexp_end(Fp12 &r, const CExp &c, const Fp &ninv) {
     inv = fp2_mul(inv, cexp_den(c.s[2]));             // 1 / (d1 d2)
     Fp2 i2 = fp2_mul(inv, c.p1);
     Fp2 i1 = fp2_mul(inv, cexp_den(c.s[1]));
-    Fp12 a, g;
+    Fp12 a, g, t;
     cexp_decompress(a, c.s[0], i1);
     cexp_decompress(g, c.s[1], i2);
-    fp12_mul(a, a, g);
-    cexp_decompress(g, c.s[2], i3);
-    fp12_mul(a, a, g);
+    fp12_mul(a, a, g);                                // f^(2^16 + 2^48)
+    cexp_decompress(g, c.s[2], i3);                   // y = f^(2^57); the top bits of |x| are 105 * 2^57
+    // y^105 = (y^7)^15 with y^7 = y^8 conj(y) and z^15 = z^16 conj(z) (conj = inverse here):
+    // 7 squarings + 2 products instead of 6 + 3 for the plain square-and-multiply
+    static_assert((ZKP_BLS_X >> ZKP_CEXP_RUN) == 105, "top bits of |x|");
+    t = g;
 #pragma unroll 1
-    for (int b = ZKP_CEXP_RUN + 1; b <= 63; b++) {
-        fp12_cyclotomic_sqr(g, g);
-        if ((ZKP_BLS_X >> b) & 1) fp12_mul(a, a, g);
-    }
+    for (int k = 0; k < 3; k++) fp12_cyclotomic_sqr(t, t);
+    fp12_conj(g, g);
+    fp12_mul(g, t, g);
+    t = g;
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) fp12_cyclotomic_sqr(t, t);
+    fp12_conj(g, g);
+    fp12_mul(g, t, g);
+    fp12_mul(a, a, g);
     fp12_conj(r, a);
 }
 
@@ -264,18 +281,23 @@ ZKP_NOINLINE void cexp_end(Fp12 &r, const CExp &c, const Fp &ninv) {
 // above).  The GPU path runs every stage as a launch with a batched inversion kernel in between
 // (Montgomery's trick across pairings: ~41 Fp products per inverse instead of a 609-product Fermat ladder
 // per lane, pairing_kernel.cu); final_exponentiation() below chains the same stages with in-lane
-// inversions (dev simulation, small helpers).  With m = the easy part's output the stages compute
-//   a = m^x, b = a^2, c = m^-2 a, d = c^x, e = d^x, g = e^x b, h = g^x
-//   result = conj(c) m . frob3(d m) . frob2(a e) . frob(g conj(m)) . h
-// -- the zkcrypto-lineage addition chain of SURVEY 9.2 with its products reassociated so that at most
-// four Fp12 (m, a, b, acc) are live across a stage boundary.
-// f must be non-zero (a Miller-loop output always is); zero maps to zero (acc carries the factor m = 0).
+// inversions (dev simulation, small helpers).
+//
+// Hard part: the lineage's addition chain raises the easy part's output m to
+//   3 (p^4 - p^2 + 1) / r  =  (x - 1)^2 (x + p) (x^2 + p^2 - 1) + 3
+// (checked with the oracle: its final_exponentiation equals m^(3h) and the identity above holds for the
+// BLS12-381 parameters), so the same field element is reached through the shorter chain of that
+// factorisation -- five f^x as before, but 7 Fp12 products instead of 10, 2 Frobenius maps instead of 3
+// and one plain cyclotomic squaring instead of 3 -- and only two Fp12 (m, y) live across a stage boundary:
+//   y1 = m^(x-1)   y2 = y1^(x-1)   y3 = y2^(x+p)   u = y3^x   result = u^x . frob2(y3) . conj(y3) . m^2 . m
+// (z^(x-1) = z^x conj(z) and conj = inverse in the cyclotomic subgroup).
+// f must be non-zero (a Miller-loop output always is); zero maps to zero (the last product carries m = 0).
 struct FeState {
     Fp6 c;   // cofactors of the Fp6 inverse
     Fp2 t;   // the Fp2 whose norm is inverted
 };
 struct FeWork {
-    Fp12 m, a, b, acc;
+    Fp12 m, y;
     CExp c;
 };
 #define ZKP_FE_STAGES 6
@@ -293,37 +315,28 @@ ZKP_HD Fp fe_stage(int stage, FeWork &w, const Fp12 *f, const FeState *s, const 
             fp12_mul(w.m, t, x);               // easy part done
             return cexp_begin(w.c, w.m);
         case 1:
-            cexp_end(w.a, w.c, ninv);
-            fp12_cyclotomic_sqr(w.b, w.a);
-            fp12_cyclotomic_sqr(t, w.m);
-            fp12_conj(t, t);                   // m^-2
-            fp12_mul(x, t, w.a);               // c
-            fp12_conj(t, x);
-            fp12_mul(w.acc, t, w.m);
-            return cexp_begin(w.c, x);
         case 2:
-            cexp_end(x, w.c, ninv);            // d
-            fp12_mul(t, x, w.m);
-            fp12_frobenius(t, t, 3);
-            fp12_mul(w.acc, w.acc, t);
-            return cexp_begin(w.c, x);
-        case 3:
-            cexp_end(x, w.c, ninv);            // e
-            fp12_mul(t, w.a, x);
-            fp12_frobenius(t, t, 2);
-            fp12_mul(w.acc, w.acc, t);
-            return cexp_begin(w.c, x);
-        case 4:
             cexp_end(x, w.c, ninv);
-            fp12_mul(x, x, w.b);               // g
-            fp12_conj(t, w.m);
-            fp12_mul(t, x, t);
-            fp12_frobenius(t, t, 1);
-            fp12_mul(w.acc, w.acc, t);
+            fp12_conj(t, stage == 1 ? w.m : w.y);
+            fp12_mul(w.y, x, t);               // y1 = m^(x-1), y2 = y1^(x-1)
+            return cexp_begin(w.c, w.y);
+        case 3:
+            cexp_end(x, w.c, ninv);
+            fp12_frobenius(t, w.y, 1);
+            fp12_mul(w.y, x, t);               // y3 = y2^(x+p)
+            return cexp_begin(w.c, w.y);
+        case 4:
+            cexp_end(x, w.c, ninv);            // u = y3^x
             return cexp_begin(w.c, x);
         default:
-            cexp_end(x, w.c, ninv);            // h
-            fp12_mul(*result, w.acc, x);
+            cexp_end(x, w.c, ninv);            // y3^(x^2)
+            fp12_frobenius(t, w.y, 2);
+            fp12_mul(x, x, t);
+            fp12_conj(t, w.y);
+            fp12_mul(x, x, t);                 // y3^(x^2 + p^2 - 1)
+            fp12_cyclotomic_sqr(t, w.m);
+            fp12_mul(x, x, t);
+            fp12_mul(*result, x, w.m);         // . m^3
             return fp_zero();
     }
 }

@@ -29,18 +29,16 @@ using namespace zkp;
 // live values in `lanes` and the pair's norm in `norm` -- internal Montgomery limbs, never seen by the
 // caller.  Layout: slot-major, lanes[slot][2 n] Fp, so that the 32 lanes of a warp touch one contiguous
 // 1536-byte run per slot (coalesced 128-bit loads/stores).  Slots (Fp per lane):
-//   0..5 m   6..11 a   12..17 b   18..23 acc   24..35 the three snapshots   36 p1   37 p2   38 t
-// stage 0's inputs reuse slots that are first written by stage 1: f in 6..11, the FeState in 12..15.
-// A stage moves only what it reads / changes: ~25 KB per pairing over the whole pipeline, 0.6 % of the
-// step at HBM speed.
-#define ZKP_FE_LANE_FP 39
+//   0..5 m   6..11 y   12..23 the three snapshots   24 p1   25 p2   26 t
+// stage 0's inputs reuse slots it overwrites itself afterwards (a lane only ever touches its own column):
+// f in 6..11, the FeState in 12..15.  A stage moves only what it reads / changes: ~16 KB per pairing over
+// the whole pipeline, 0.4 % of the step at HBM speed.
+#define ZKP_FE_LANE_FP 27
 #define ZKP_SLOT_M 0
-#define ZKP_SLOT_A 6
-#define ZKP_SLOT_B 12
-#define ZKP_SLOT_ACC 18
-#define ZKP_SLOT_CEXP 24
-#define ZKP_SLOT_F ZKP_SLOT_A
-#define ZKP_SLOT_FES ZKP_SLOT_B
+#define ZKP_SLOT_Y 6
+#define ZKP_SLOT_CEXP 12
+#define ZKP_SLOT_F ZKP_SLOT_Y
+#define ZKP_SLOT_FES ZKP_SLOT_CEXP
 struct FeScratch {
     Fp *lanes;   // [ZKP_FE_LANE_FP][2 * n]
     Fp *norm;    // [n], replaced by its inverse in place
@@ -142,10 +140,8 @@ k_fe_stage(int stage, FeScratch fs, uint64_t *__restrict__ out, uint8_t *__restr
         s.t.c = fs.lanes[(size_t)(ZKP_SLOT_FES + 3) * fs.n2 + lane];
     } else {
         fetch_cexp(fs, lane, w.c);
-        if (stage != 1) fetch_fp12(fs, lane, ZKP_SLOT_ACC, w.acc);
-        if (stage == 1 || stage == 2 || stage == 4) fetch_fp12(fs, lane, ZKP_SLOT_M, w.m);
-        if (stage == 3) fetch_fp12(fs, lane, ZKP_SLOT_A, w.a);
-        if (stage == 4) fetch_fp12(fs, lane, ZKP_SLOT_B, w.b);
+        if (stage == 1 || stage == ZKP_FE_STAGES - 1) fetch_fp12(fs, lane, ZKP_SLOT_M, w.m);
+        if (stage == 2 || stage == 3 || stage == ZKP_FE_STAGES - 1) fetch_fp12(fs, lane, ZKP_SLOT_Y, w.y);
     }
     Fp ninv = fs.norm[i];
     Fp nrm = fe_stage(stage, w, &f, &s, ninv, &f);
@@ -157,11 +153,7 @@ k_fe_stage(int stage, FeScratch fs, uint64_t *__restrict__ out, uint8_t *__restr
     if (live) {
         park_cexp(fs, lane, w.c);
         if (stage == 0) park_fp12(fs, lane, ZKP_SLOT_M, w.m);
-        if (stage == 1) {
-            park_fp12(fs, lane, ZKP_SLOT_A, w.a);
-            park_fp12(fs, lane, ZKP_SLOT_B, w.b);
-        }
-        if (stage >= 1) park_fp12(fs, lane, ZKP_SLOT_ACC, w.acc);
+        if (stage >= 1 && stage <= 3) park_fp12(fs, lane, ZKP_SLOT_Y, w.y);
         if (lane_par() == 0) fs.norm[i] = nrm;
     }
 }
