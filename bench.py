@@ -31,12 +31,12 @@ MACS_PER_FP_MUL = 300
 MACS_PER_PAIRING = FP_MULS_PER_PAIRING * MACS_PER_FP_MUL
 IO_BYTES_PER_PAIRING = 288 + 576
 # wide MACs the kernels really execute per pairing, both lanes together: 2 x (288+156) per Fp2 product,
-# 2 x 300 per Fp2 square, 300 per Fp product.  The dev simulation counts 6,068,808 for the one-call
+# 2 x 300 per Fp2 square, 300 per Fp product.  The dev simulation counts 6,055,488 for the one-call
 # path (tests/test_host_logic.py::test_sim_executed_mac_count), which runs the six Fp inversions of the
 # final exponentiation (easy part + one per compressed f^x) as in-lane Fermat ladders (6 x 364,800); the
 # GPU path replaces each by a batched inversion (656 products per run of 16 = 12,300 per pairing) and
 # adds 20 boundary conversions x 300.
-EXECUTED_MACS_PER_PAIRING = 6_068_808 - 6 * 364_800 + 6 * 12_300 + 6_000
+EXECUTED_MACS_PER_PAIRING = 6_055_488 - 6 * 364_800 + 6 * 12_300 + 6_000
 
 
 def hbm_peak():
@@ -284,7 +284,7 @@ def run_ours(args):
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": "2^%d independent random BLS12-381 pairings per GPU (a_i*G1gen, b_i*G2gen; Miller loop + final "
-                                   "exponentiation with compressed squarings: 13 launches per step)" % args.log2_batch,
+                                   "exponentiation with compressed squarings: 1 + 2 x 6 x (batched inversion + stage) launches per step)" % args.log2_batch,
                        "pairings_per_gpu_per_step": n, "parallelism": "independent pairings sharded one slice per GPU, no collective",
                        "l2": "inputs+outputs per step = %.0f MB > 126 MB L2; kernel is integer-bound, not cache sensitive" % (n * IO_BYTES_PER_PAIRING / 1e6),
                        "engine": eng.version()},
@@ -294,9 +294,10 @@ def run_ours(args):
             "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T wide-MAC/s",
                          "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of the step's launches in the ncu --set
-                         # full capture of a 2^16 step (profiles/r1h_ncu_summary.txt: 4.50 GB), scaled to this batch
-                         "traffic": 4.50e9 * n / 65536.0,
-                         "kernel": "k_pairing<1> + 6 x (k_fe_batch_inv + k_fe_stage) (one step)", "kernel_ms": per_launch_ms, "algorithmic_macs_per_pairing": MACS_PER_PAIRING,
+                         # full capture of a 2^16 step (profiles/r1k_ncu_summary.txt: 8.27 GB, thread-local frames
+                         # written back past L2), scaled to this batch
+                         "traffic": 8.27e9 * n / 65536.0,
+                         "kernel": "k_pairing<1> + 2 halves x 6 x (k_fe_batch_inv + k_fe_stage) (one step)", "kernel_ms": per_launch_ms, "algorithmic_macs_per_pairing": MACS_PER_PAIRING,
                          "executed_macs_per_pairing": EXECUTED_MACS_PER_PAIRING,
                          "executed_frac": pairs_per_s_kernel * EXECUTED_MACS_PER_PAIRING / peak,
                          "peak_source": "measured in this run (zkp_imad_peak): max of independent IMAD.WIDE.U32 chains and the "

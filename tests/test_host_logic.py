@@ -285,12 +285,12 @@ def test_sim_executed_mac_count(sim, coracle):
     fexp = sim.sim_take_mac_count()
     sim.sim_pairing(3, _p(g1), None, _p(g2), None, ctypes.c_size_t(1), 4, None, _p(out), None)
     check4 = sim.sim_take_mac_count()
-    assert (miller, fexp, check4) == (2041032, 4027776, 10244520)   # the one-call path runs SIX in-lane Fermat ladders
+    assert (miller, fexp, check4) == (2041032, 4014456, 10231200)   # the one-call path runs SIX in-lane Fermat ladders
     a, o, st = util.random_fp_matrix(1, 1, seed=3), np.zeros((1, 6), np.uint64), np.zeros(1, np.uint8)
     sim.sim_tower_op(5, _p(a), None, _p(o), _p(st), ctypes.c_size_t(1))
     assert sim.sim_take_mac_count() == 364800        # the Fermat ladder both lanes would run: 2 x 608 x 300
     sys_path = os.path.join(ROOT, "bench.py")
-    assert "6_068_808" in open(sys_path).read() and miller + fexp == 6068808
+    assert "6_055_488" in open(sys_path).read() and miller + fexp == 6055488
 
 
 def test_sim_operand_bounds_are_asserted(sim):

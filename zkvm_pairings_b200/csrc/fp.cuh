@@ -124,6 +124,15 @@ template <int PAR>
 ZKP_HD uint32_t word_bcast(uint32_t v) { uint32_t o = zkp_sim_word_xchg(v); return zkp_sim_par == PAR ? v : o; }
 #endif
 ZKP_HD bool lane_or(bool x) { return (x | (word_xchg(x ? 1u : 0u) != 0)); }
+// true when x holds in any lane that shares this lane's control flow: the whole warp in the converged
+// kernels, the lane pair elsewhere -- i.e. a predicate every such lane may branch on together
+ZKP_HD bool group_any(bool x) {
+#if defined(ZKP_DEVICE_BUILD) && defined(ZKP_CONVERGED)
+    return __any_sync(0xffffffffu, x) != 0;
+#else
+    return lane_or(x);
+#endif
+}
 ZKP_HD bool lane_and(bool x) { return (x & (word_xchg(x ? 1u : 0u) != 0)); }
 
 // ------------------------------------------------------------------ constants / trivial ops

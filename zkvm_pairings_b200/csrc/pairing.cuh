@@ -235,8 +235,10 @@ ZKP_NOINLINE Fp cexp_begin(CExp &c, const Fp12 &f) {
 ZKP_NOINLINE void cexp_decompress(Fp12 &g, const Fp2 *z, const Fp2 &dinv) {
     Fp2 s4 = fp2_sqr(z[2]);
     Fp2 num_a = fp2_sub(fp2_add(fp2_mul_nr(fp2_sqr(z[3])), fp2_add(fp2_dbl(s4), s4)), fp2_dbl(z[1]));
-    Fp2 num_b = fp2_dbl(fp2_mul(z[2], z[3]));
-    Fp2 z1 = fp2_mul(fp2_select(fp2_is_zero(z[0]), num_b, num_a), dinv);
+    bool z2z = fp2_is_zero(z[0]);
+    Fp2 num = num_a;
+    if (group_any(z2z)) num = fp2_select(z2z, fp2_dbl(fp2_mul(z[2], z[3])), num_a);   // (never taken on valid data)
+    Fp2 z1 = fp2_mul(num, dinv);
     Fp2 m = fp2_mul(z[1], z[2]);
     Fp2 t = fp2_add(fp2_dbl(fp2_sqr(z1)), fp2_mul(z[0], z[3]));   // z2 z5 vanishes by itself when z2 = 0
     t = fp2_sub(t, fp2_add(fp2_dbl(m), m));

@@ -15,6 +15,9 @@
 #ifndef ZKP_MIN_BLOCKS
 #define ZKP_MIN_BLOCKS 2      // resident blocks per SM the register allocator must allow (Miller kernel)
 #endif
+#ifndef ZKP_FE_SPLIT_MIN
+#define ZKP_FE_SPLIT_MIN ((size_t)1 << 15)   // checks; smaller batches run their final exponentiation as one piece
+#endif
 #ifndef ZKP_MIN_BLOCKS_FE
 #define ZKP_MIN_BLOCKS_FE 3   // same for the final-exponentiation kernel (measured: 93.9 ms vs 96.4 at 2, 2^18)
 #endif
@@ -124,8 +127,9 @@ __global__ void __launch_bounds__(128) k_fe_batch_inv(Fp *norm, size_t n) {
 // one stage of the final exponentiation (pairing.cuh fe_stage): consumes the inverse the preceding
 // k_fe_batch_inv left in norm[i], leaves the next norm there; the last stage stores the result
 __global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS_FE)
-k_fe_stage(int stage, FeScratch fs, uint64_t *__restrict__ out, uint8_t *__restrict__ is_one, size_t n) {
-    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+k_fe_stage(int stage, FeScratch fs, uint64_t *__restrict__ out, uint8_t *__restrict__ is_one, size_t i0, size_t n) {
+    // this launch covers the checks [i0, n) of the batch
+    size_t i = i0 + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1);
     bool live = i < n;
     if (!live) i = n - 1;
     size_t lane = 2 * i + lane_par();
@@ -178,12 +182,41 @@ cudaError_t zkp_launch_k_pairing(int mode, const uint64_t *g1, const uint8_t *g1
     }
     *launches = 1;
     if (mode & ZKP_DO_FINAL_EXP) {
-        size_t threads = (n + ZKP_INV_RUN - 1) / ZKP_INV_RUN;
-        for (int stage = 0; stage < ZKP_FE_STAGES; stage++) {
-            k_fe_batch_inv<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(fs.norm, n);
-            k_fe_stage<<<g, b, 0, st>>>(stage, fs, out, is_one, n);
+        // The batch runs as two halves on two streams: while one half is in its (latency-bound) batched
+        // inversion or in the tail of a stage kernel, the other half's stage kernel keeps the SMs busy.
+        size_t na = n, nb = 0;
+        if (n >= ZKP_FE_SPLIT_MIN) {
+            na = ((n / 2) + 63) & ~(size_t)63;
+            nb = n - na;
         }
-        *launches = 1 + 2 * ZKP_FE_STAGES;
+        cudaStream_t s2 = nullptr;
+        cudaEvent_t fork = nullptr, join = nullptr;
+        if (nb) {
+            cudaError_t e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(fork, st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s2, fork, 0);
+            if (e != cudaSuccess) return e;
+        }
+        dim3 ga((unsigned)((2 * na + ZKP_TPB - 1) / ZKP_TPB)), gb((unsigned)((2 * nb + ZKP_TPB - 1) / ZKP_TPB));
+        size_t ta = (na + ZKP_INV_RUN - 1) / ZKP_INV_RUN, tb = (nb + ZKP_INV_RUN - 1) / ZKP_INV_RUN;
+        for (int stage = 0; stage < ZKP_FE_STAGES; stage++) {
+            k_fe_batch_inv<<<(unsigned)((ta + 127) / 128), 128, 0, st>>>(fs.norm, na);
+            k_fe_stage<<<ga, b, 0, st>>>(stage, fs, out, is_one, 0, na);
+            if (nb) {
+                k_fe_batch_inv<<<(unsigned)((tb + 127) / 128), 128, 0, s2>>>(fs.norm + na, nb);
+                k_fe_stage<<<gb, b, 0, s2>>>(stage, fs, out, is_one, na, n);
+            }
+        }
+        *launches = 1 + 2 * ZKP_FE_STAGES * (nb ? 2 : 1);
+        if (nb) {
+            cudaEventRecord(join, s2);
+            cudaStreamWaitEvent(st, join, 0);
+            cudaEventDestroy(fork);
+            cudaEventDestroy(join);
+            cudaStreamDestroy(s2);   // returns at once; the stream's resources go when its work has drained
+        }
     }
     return cudaGetLastError();
 }
