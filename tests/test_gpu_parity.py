@@ -238,6 +238,23 @@ def test_full_size_final_exp_config2_properties(engine, coracle, pyref):
     assert np.array_equal(fe[idx], coracle.final_exp_batch(ml[idx]))
 
 
+def test_final_exponentiation_edge_inputs(engine, coracle, pyref):
+    """Staged final exponentiation on inputs that are not Miller-loop outputs: zero, one, subfield elements
+    (every decompression takes its degenerate branch), random Fp12; a ragged batch so that tail lanes and the
+    two-stream split boundary are exercised too."""
+    f = util.final_exp_edge_inputs(n_random=23)
+    out = engine.final_exponentiation_batch(f)
+    assert np.array_equal(out, coracle.final_exp_batch(f))
+    assert not out[0].any()
+    assert util.arr_to_fp12(out[1]) == pyref.FP12_ONE and util.arr_to_fp12(out[5]) == pyref.FP12_ONE
+    # the same rows tiled past the split threshold (2^15 checks): both halves, odd size
+    n = (1 << 15) + 77
+    big = np.ascontiguousarray(np.tile(f, (n // f.shape[0] + 1, 1))[:n])
+    outb = engine.final_exponentiation_batch(big)
+    assert np.array_equal(outb[: f.shape[0]], out) and np.array_equal(outb[-f.shape[0]:], coracle.final_exp_batch(big[-f.shape[0]:]))
+    assert np.array_equal(outb[n // 2 - 40: n // 2 + 40], coracle.final_exp_batch(big[n // 2 - 40: n // 2 + 40]))
+
+
 def test_device_resident_path(engine, coracle):
     import torch
     n = 512

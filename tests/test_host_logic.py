@@ -256,6 +256,23 @@ def test_sim_prepared_g2_tables(sim, coracle):
     assert np.array_equal(out2, exp2)
 
 
+def test_sim_final_exponentiation_edge_inputs(sim, coracle, pyref):
+    """The staged final exponentiation (compressed squarings, factorised hard part) on inputs that are not
+    Miller-loop outputs -- zero, one, subfield elements (degenerate decompression), random Fp12 -- against the
+    C oracle's plain Granger-Scott chain, and against the big-int oracle on two of them."""
+    f = util.final_exp_edge_inputs()
+    n = f.shape[0]
+    out = np.zeros((n, 72), np.uint64)
+    one = np.zeros(n, np.uint8)
+    assert sim.sim_pairing(2, None, None, None, None, ctypes.c_size_t(n), 1, _p(f), _p(out), _p(one)) == 0
+    exp = coracle.final_exp_batch(f)
+    assert np.array_equal(out, exp)
+    assert not out[0].any()                                   # zero maps to zero
+    assert list(one[:6]) == [0, 1, 1, 1, 1, 1]                # subfield elements die in the easy part
+    for j in (7, n - 1):
+        assert util.arr_to_fp12(out[j]) == pyref.final_exponentiation(util.arr_to_fp12(f[j]))
+
+
 def test_sim_batch_inversion(sim, coracle, pyref):
     """fp_batch_inv (Montgomery's trick, used between the two final-exponentiation launches): equal to
     element-wise Fermat inversion, zeros stay zero and do not poison their run, ragged last run."""

@@ -197,3 +197,18 @@ def pow_sqrt_case(pyref, name, n, seed):
         else:
             exp.append(fp12_to_arr(pyref.fp12_pow_vartime(arr_to_fp12(row), by)))
     return a, b, np.stack(exp), np.zeros(n, np.uint8)
+
+
+def final_exp_edge_inputs(seed=11, n_random=6):
+    """Fp12 inputs for the final exponentiation that are NOT Miller-loop outputs: zero (maps to zero), one, -1,
+    elements of the subfields Fp / Fp2 / Fp6 (the easy part sends them to one, so every f^x of the hard part
+    runs the degenerate z2 = z3 = 0 decompression), a pure-w element, and random field elements."""
+    rng = random.Random(seed)
+    z = [0] * 12
+    rows = [z[:], [1] + z[1:], [o.P - 1] + z[1:], [rng.randrange(1, o.P)] + z[1:],
+            [rng.randrange(o.P), rng.randrange(o.P)] + z[2:],                       # Fp2
+            [rng.randrange(o.P) for _ in range(6)] + z[6:],                         # Fp6 (c1 = 0)
+            z[:6] + [rng.randrange(o.P) for _ in range(6)],                         # c0 = 0
+            z[:6] + [1] + z[7:]]                                                    # w
+    rows += [[rng.randrange(o.P) for _ in range(12)] for _ in range(n_random)]
+    return np.stack([fp_arr(r) for r in rows])
