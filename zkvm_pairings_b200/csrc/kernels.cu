@@ -237,7 +237,37 @@ struct DevBuf {
     }
 };
 
-enum { B_G1 = 0, B_G1INF, B_G2, B_G2INF, B_IN, B_OUT, B_FLAG, B_TAB, B_NBUF };
+// pinned host staging for user buffers that are pageable (a plain Vec / numpy array): an async copy to or
+// from pageable memory blocks the issuing thread until it is done, which would serialise the two buffer
+// sets of the pipeline; staged through these, the copies of one set overlap the kernels of the other
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+struct PendingOut {   // staged device->host copy still to be moved into the caller's buffer
+    void *user;
+    const void *stage;
+    size_t bytes;
+};
+
+enum { B_G1 = 0, B_G1INF, B_G2, B_G2INF, B_IN, B_OUT, B_FLAG, B_TAB, B_NBUF, B_TABINF = B_NBUF, B_NPIN };
+#ifndef ZKP_STAGE_MIN
+#define ZKP_STAGE_MIN ((size_t)256 << 10)   // smaller transfers go straight from / to the caller's memory
+#endif
 
 struct DevState {
     int id = 0;
@@ -246,6 +276,8 @@ struct DevState {
     uint32_t *d_err = nullptr;
     cudaMemPool_t pool = nullptr;   // stream-ordered scratch of the final exponentiation (kept, never trimmed)
     DevBuf buf[2][B_NBUF];     // double-buffered pipeline scratch
+    PinBuf pin_in[2][B_NPIN], pin_out[2][B_NPIN];   // pinned staging per buffer set (only for pageable user buffers)
+    std::vector<PendingOut> pend[2];
     DevBuf scratch, partial;   // product reduction
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timers;
     double timed_ms = 0;
@@ -400,6 +432,10 @@ void zkp_ctx_destroy(zkp_ctx *ctx) {
         }
         for (int s = 0; s < 2; s++) {
             for (int b = 0; b < B_NBUF; b++) d.buf[s][b].release();
+            for (int b = 0; b < B_NPIN; b++) {
+                d.pin_in[s][b].release();
+                d.pin_out[s][b].release();
+            }
             if (d.stream[s]) cudaStreamDestroy(d.stream[s]);
         }
         d.scratch.release();
@@ -559,49 +595,85 @@ static int32_t run_slice(zkp_ctx *ctx, DevState &d, const HostJob &j, size_t lo,
     if (j.mode == 16) tower_op_shape(j.op, na, nb, nr);
     size_t chunk = ZKP_CHUNK;
     int s = 0;
+    cudaStream_t st = nullptr;
+    d.pend[0].clear();   // (a job that failed half-way leaves nothing behind for the next one)
+    d.pend[1].clear();
+    auto pageable = [](const void *p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+            cudaGetLastError();
+            return true;
+        }
+        return a.type == cudaMemoryTypeUnregistered;
+    };
+    auto h2d = [&](int which, void *dst, const void *src, size_t bytes) -> cudaError_t {
+        if (bytes >= ZKP_STAGE_MIN && pageable(src)) {
+            PinBuf &pb = d.pin_in[s][which];
+            cudaError_t e = pb.ensure(bytes);
+            if (e != cudaSuccess) return e;
+            memcpy(pb.p, src, bytes);
+            src = pb.p;
+        }
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    };
+    auto d2h = [&](int which, void *dst, const void *src, size_t bytes) -> cudaError_t {
+        if (bytes >= ZKP_STAGE_MIN && pageable(dst)) {
+            PinBuf &pb = d.pin_out[s][which];
+            cudaError_t e = pb.ensure(bytes);
+            if (e != cudaSuccess) return e;
+            d.pend[s].push_back(PendingOut{dst, pb.p, bytes});
+            dst = pb.p;
+        }
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+    };
+    auto flush = [&](int set) {   // after that set's stream has drained
+        for (const PendingOut &o : d.pend[set]) memcpy(o.user, o.stage, o.bytes);
+        d.pend[set].clear();
+    };
     for (size_t c0 = lo; c0 < hi; c0 += chunk, s ^= 1) {
         size_t cn = hi - c0 < chunk ? hi - c0 : chunk;
-        cudaStream_t st = d.stream[s];
+        st = d.stream[s];
         DevBuf *B = d.buf[s];
         CUS(cudaStreamSynchronize(st));   // this buffer set's previous chunk is fully drained
+        flush(s);
         if (j.mode == 16) {
             CUS(B[B_IN].ensure(cn * na * 48));
             CUS(B[B_OUT].ensure(cn * nr * 48));
             CUS(B[B_FLAG].ensure(cn));
-            CUS(cudaMemcpyAsync(B[B_IN].p, j.a + c0 * na * 6, cn * na * 48, cudaMemcpyHostToDevice, st));
+            CUS(h2d(B_IN, B[B_IN].p, j.a + c0 * na * 6, cn * na * 48));
             if (nb) {
                 CUS(B[B_G2].ensure(cn * nb * 48));
-                CUS(cudaMemcpyAsync(B[B_G2].p, j.b + c0 * nb * 6, cn * nb * 48, cudaMemcpyHostToDevice, st));
+                CUS(h2d(B_G2, B[B_G2].p, j.b + c0 * nb * 6, cn * nb * 48));
             }
             k_tower_op<<<grid_for(cn), ZKP_TPB, 0, st>>>(j.op, (const uint64_t *)B[B_IN].p, nb ? (const uint64_t *)B[B_G2].p : nullptr,
                                                         (uint64_t *)B[B_OUT].p, (uint8_t *)B[B_FLAG].p, d.d_err, cn);
             ctx->launches++;
             CUS(cudaGetLastError());
-            CUS(cudaMemcpyAsync(j.out + c0 * nr * 6, B[B_OUT].p, cn * nr * 48, cudaMemcpyDeviceToHost, st));
-            if (j.flags) CUS(cudaMemcpyAsync(j.flags + c0, B[B_FLAG].p, cn, cudaMemcpyDeviceToHost, st));
+            CUS(d2h(B_OUT, j.out + c0 * nr * 6, B[B_OUT].p, cn * nr * 48));
+            if (j.flags) CUS(d2h(B_FLAG, j.flags + c0, B[B_FLAG].p, cn));
         } else if (j.mode == 48) {
             const size_t w = (j.op & 1) ? 24 : 12;
             const bool is_mul = j.op >= GOP_G1_MUL;
             CUS(B[B_IN].ensure(cn * w * 8));
             CUS(B[B_FLAG].ensure(cn));
-            CUS(cudaMemcpyAsync(B[B_IN].p, j.pts + c0 * w, cn * w * 8, cudaMemcpyHostToDevice, st));
+            CUS(h2d(B_IN, B[B_IN].p, j.pts + c0 * w, cn * w * 8));
             const uint8_t *dinf = nullptr;
             if (j.g1inf) {
                 CUS(B[B_G1INF].ensure(cn));
-                CUS(cudaMemcpyAsync(B[B_G1INF].p, j.g1inf + c0, cn, cudaMemcpyHostToDevice, st));
+                CUS(h2d(B_G1INF, B[B_G1INF].p, j.g1inf + c0, cn));
                 dinf = (const uint8_t *)B[B_G1INF].p;
             }
             if (is_mul) {
                 CUS(B[B_G2].ensure(cn * 32));
                 CUS(B[B_OUT].ensure(cn * w * 8));
-                CUS(cudaMemcpyAsync(B[B_G2].p, j.scalars + c0 * 4, cn * 32, cudaMemcpyHostToDevice, st));
+                CUS(h2d(B_G2, B[B_G2].p, j.scalars + c0 * 4, cn * 32));
             }
             k_group_op<<<grid_for(cn), ZKP_TPB, 0, st>>>(j.op, (const uint64_t *)B[B_IN].p, dinf, is_mul ? (const uint64_t *)B[B_G2].p : nullptr,
                                                         is_mul ? (uint64_t *)B[B_OUT].p : nullptr, (uint8_t *)B[B_FLAG].p, d.d_err, cn);
             ctx->launches++;
             CUS(cudaGetLastError());
-            if (is_mul) CUS(cudaMemcpyAsync(j.out + c0 * w, B[B_OUT].p, cn * w * 8, cudaMemcpyDeviceToHost, st));
-            CUS(cudaMemcpyAsync(j.flags + c0, B[B_FLAG].p, cn, cudaMemcpyDeviceToHost, st));
+            if (is_mul) CUS(d2h(B_OUT, j.out + c0 * w, B[B_OUT].p, cn * w * 8));
+            CUS(d2h(B_FLAG, j.flags + c0, B[B_FLAG].p, cn));
         } else if (j.mode == 32) {
             CUS(B[B_G1].ensure(cn * 96));
             CUS(B[B_G2].ensure(cn * 192));
@@ -611,10 +683,10 @@ static int32_t run_slice(zkp_ctx *ctx, DevState &d, const HostJob &j, size_t lo,
                                                           (uint64_t *)B[B_G2].p, (uint8_t *)B[B_G2INF].p);
             ctx->launches++;
             CUS(cudaGetLastError());
-            CUS(cudaMemcpyAsync(j.og1 + c0 * 12, B[B_G1].p, cn * 96, cudaMemcpyDeviceToHost, st));
-            CUS(cudaMemcpyAsync(j.og2 + c0 * 24, B[B_G2].p, cn * 192, cudaMemcpyDeviceToHost, st));
-            CUS(cudaMemcpyAsync(j.og1inf + c0, B[B_G1INF].p, cn, cudaMemcpyDeviceToHost, st));
-            CUS(cudaMemcpyAsync(j.og2inf + c0, B[B_G2INF].p, cn, cudaMemcpyDeviceToHost, st));
+            CUS(d2h(B_G1, j.og1 + c0 * 12, B[B_G1].p, cn * 96));
+            CUS(d2h(B_G2, j.og2 + c0 * 24, B[B_G2].p, cn * 192));
+            CUS(d2h(B_G1INF, j.og1inf + c0, B[B_G1INF].p, cn));
+            CUS(d2h(B_G2INF, j.og2inf + c0, B[B_G2INF].p, cn));
         } else {
             size_t np = cn * (size_t)j.k, p0 = c0 * (size_t)j.k;
             size_t nq = cn * (size_t)(j.k - j.kf), q0 = c0 * (size_t)(j.k - j.kf);   // per-check G2 points
@@ -622,42 +694,44 @@ static int32_t run_slice(zkp_ctx *ctx, DevState &d, const HostJob &j, size_t lo,
             if (j.mode & 1) {
                 CUS(B[B_G1].ensure(np * 96));
                 CUS(B[B_G2].ensure(nq * 192 + 16));
-                CUS(cudaMemcpyAsync(B[B_G1].p, j.g1 + p0 * 12, np * 96, cudaMemcpyHostToDevice, st));
-                if (nq) CUS(cudaMemcpyAsync(B[B_G2].p, j.g2 + q0 * 24, nq * 192, cudaMemcpyHostToDevice, st));
+                CUS(h2d(B_G1, B[B_G1].p, j.g1 + p0 * 12, np * 96));
+                if (nq) CUS(h2d(B_G2, B[B_G2].p, j.g2 + q0 * 24, nq * 192));
                 if (j.kf) {
                     size_t tb = (size_t)j.kf * ZKP_LINE_STEPS * 3 * 2 * sizeof(Fp);
                     CUS(B[B_TAB].ensure(tb + 16));
-                    CUS(cudaMemcpyAsync(B[B_TAB].p, j.tab, tb, cudaMemcpyHostToDevice, st));
+                    CUS(h2d(B_TAB, B[B_TAB].p, j.tab, tb));
                     if (j.tabinf) {
-                        CUS(cudaMemcpyAsync((uint8_t *)B[B_TAB].p + tb, j.tabinf, j.kf, cudaMemcpyHostToDevice, st));
+                        CUS(h2d(B_TABINF, (uint8_t *)B[B_TAB].p + tb, j.tabinf, j.kf));
                         dti = (const uint8_t *)B[B_TAB].p + tb;
                     }
                 }
                 if (j.g1inf) {
                     CUS(B[B_G1INF].ensure(np));
-                    CUS(cudaMemcpyAsync(B[B_G1INF].p, j.g1inf + p0, np, cudaMemcpyHostToDevice, st));
+                    CUS(h2d(B_G1INF, B[B_G1INF].p, j.g1inf + p0, np));
                     di1 = (const uint8_t *)B[B_G1INF].p;
                 }
                 if (j.g2inf && nq) {
                     CUS(B[B_G2INF].ensure(nq));
-                    CUS(cudaMemcpyAsync(B[B_G2INF].p, j.g2inf + q0, nq, cudaMemcpyHostToDevice, st));
+                    CUS(h2d(B_G2INF, B[B_G2INF].p, j.g2inf + q0, nq));
                     di2 = (const uint8_t *)B[B_G2INF].p;
                 }
             } else {
                 CUS(B[B_IN].ensure(cn * 576));
-                CUS(cudaMemcpyAsync(B[B_IN].p, j.in12 + c0 * 72, cn * 576, cudaMemcpyHostToDevice, st));
+                CUS(h2d(B_IN, B[B_IN].p, j.in12 + c0 * 72, cn * 576));
             }
             CUS(B[B_OUT].ensure(cn * 576));
             if (j.flags) CUS(B[B_FLAG].ensure(cn));
             CUS(launch_pairing(ctx, d, j.mode, (const uint64_t *)B[B_G1].p, di1, (const uint64_t *)B[B_G2].p, di2, cn, j.k,
                                (const uint64_t *)B[B_IN].p, (uint64_t *)B[B_OUT].p, j.flags ? (uint8_t *)B[B_FLAG].p : nullptr,
                                d.d_err, st, j.kf ? B[B_TAB].p : nullptr, dti, j.kf));
-            CUS(cudaMemcpyAsync(j.out + c0 * 72, B[B_OUT].p, cn * 576, cudaMemcpyDeviceToHost, st));
-            if (j.flags) CUS(cudaMemcpyAsync(j.flags + c0, B[B_FLAG].p, cn, cudaMemcpyDeviceToHost, st));
+            CUS(d2h(B_OUT, j.out + c0 * 72, B[B_OUT].p, cn * 576));
+            if (j.flags) CUS(d2h(B_FLAG, j.flags + c0, B[B_FLAG].p, cn));
         }
     }
     CUS(cudaStreamSynchronize(d.stream[0]));
+    flush(0);
     CUS(cudaStreamSynchronize(d.stream[1]));
+    flush(1);
     uint32_t herr = 0;
     CUS(cudaMemcpy(&herr, d.d_err, sizeof herr, cudaMemcpyDeviceToHost));
     if (herr & 1) {

@@ -182,9 +182,11 @@ class PairingEngine:
         self._check(self._lib.zkp_final_exp_batch(self._ctx, _ptr(f), f.shape[0], _ptr(out)))
         return out
 
-    def pairing_batch(self, g1, g2, g1_inf=None, g2_inf=None):
+    def pairing_batch(self, g1, g2, g1_inf=None, g2_inf=None, out=None):
         g1, g2, i1, i2, n = self._points(g1, g2, g1_inf, g2_inf)
-        out = np.empty((n, 72), dtype=np.uint64)
+        if out is None:
+            out = np.empty((n, 72), dtype=np.uint64)
+        assert out.shape == (n, 72) and out.dtype == np.uint64 and out.flags.c_contiguous
         self._check(self._lib.zkp_pairing_batch(self._ctx, _ptr(g1), _ptr(i1), _ptr(g2), _ptr(i2), n, _ptr(out)))
         return out
 
