@@ -253,25 +253,6 @@ ZKP_HD Fp fp_select(bool c, const Fp &a, const Fp &b) {
 // by 2^32; instead of shifting registers the arrays swap roles (the old odd array is the new even
 // one, the old even array moves down 64 bits inside the first chain of the next row).
 
-// v + CF: the carry left by the preceding chain, absorbed into the top word of the other accumulator
-#if defined(ZKP_DEVICE_BUILD) && defined(ZKP_CARRY_VARIANT)
-ZKP_HD uint32_t carry_into(uint32_t v) {
-#if ZKP_CARRY_VARIANT == 1
-    uint32_t c = addc(0, 0);
-    return v + c;
-#elif ZKP_CARRY_VARIANT == 2
-    uint32_t r;
-    asm volatile("{ .reg .u32 t; addc.u32 t, 0, 0; add.u32 %0, %1, t; }" : "=r"(r) : "r"(v));
-    return r;
-#else
-    uint32_t r;
-    asm volatile("{ .reg .u32 t; .reg .pred q; addc.u32 t, 0, 0; setp.ne.u32 q, t, 0; @q add.u32 %0, %1, 1; @!q mov.u32 %0, %1; }" : "=r"(r) : "r"(v));
-    return r;
-#endif
-}
-#else
-ZKP_HD uint32_t carry_into(uint32_t v) { return addc(v, 0); }
-#endif
 // x[j..j+1] += k[j+OFF]*m for j = 0,2,..,10 (one carry chain, 6 wide MACs); leaves carry-out in CF
 template <int OFF>
 ZKP_HD void chain_mad(uint32_t *x, const uint32_t *k, uint32_t m) {
@@ -299,7 +280,7 @@ ZKP_HD void chain_mad_rshift(uint32_t *y, const uint32_t *a, uint32_t m) {
 ZKP_HD void row_mad(uint32_t *x, uint32_t *y, const uint32_t *k, uint32_t m) {
     chain_mad<1>(y, k, m);
     chain_mad<0>(x, k, m);
-    y[ZKP_NL - 1] = carry_into(y[ZKP_NL - 1]);
+    y[ZKP_NL - 1] = addc(y[ZKP_NL - 1], 0);
 }
 // reduction half of a row: m = x0 * n0'; x/y += p*m
 ZKP_HD void row_reduce(uint32_t *x, uint32_t *y) {
@@ -323,7 +304,7 @@ ZKP_HD void row_next(uint32_t *x, uint32_t *y, const uint32_t *a, uint32_t bi) {
     x[0] = add_cc(x[0], y[1]);
     chain_mad_rshift(y, a, bi);
     chain_mad<0>(x, a, bi);
-    y[ZKP_NL - 1] = carry_into(y[ZKP_NL - 1]);
+    y[ZKP_NL - 1] = addc(y[ZKP_NL - 1], 0);
 }
 // after row 11 the even role is `od` (od[0] == 0): T = ev + (od >> 32)
 ZKP_HD Fp mont_finish(const uint32_t *ev, const uint32_t *od) {
