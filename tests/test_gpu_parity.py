@@ -222,6 +222,33 @@ def test_full_size_config1_bit_exact(engine, coracle):
     assert np.array_equal(engine.final_exponentiation_batch(prod[None])[0], gt_prod)
 
 
+def test_metric_batch_2p20_properties(engine, coracle):
+    """The metric's batch (2^20 pairings on one GPU) through size-independent properties, every element checked:
+    bilinearity e([2]P, Q) == e(P, Q)^2 with [2]P from the group kernel and the square from the tower kernel,
+    "checksum of checksums" prod_i e(P_i, Q_i) == final_exp(prod_i miller(P_i, Q_i)) through the product
+    kernels, and a strided sample against the oracle."""
+    import torch
+    n = 1 << int(os.environ.get("ZKP_TEST_METRIC_LOG2", "20"))
+    g1, i1, g2, i2 = engine.gen_points(0x2B200, 0, n)
+    gt = engine.pairing_batch(g1, g2)
+    two = np.zeros((n, 4), np.uint64)
+    two[:, 0] = 2
+    g1x2, inf2 = engine.g1_mul_batch(g1, two)
+    assert not inf2.any()
+    gt2 = engine.pairing_batch(g1x2, g2)
+    assert np.array_equal(gt2, engine.tower_op("fp12_sqr", gt))
+    idx = np.arange(0, n, n // 64)
+    assert np.array_equal(gt[idx], coracle.pairing_batch(np.ascontiguousarray(g1[idx]), None, np.ascontiguousarray(g2[idx]), None))
+    _, gt_prod = engine.multi_miller_product(g1, g2)
+    st = torch.cuda.current_stream().cuda_stream
+    d_in = torch.from_numpy(gt.view(np.int64)).cuda()
+    scratch = torch.empty(engine.product_scratch_elems(n) * 72, dtype=torch.int64, device="cuda")
+    d_out = torch.empty(72, dtype=torch.int64, device="cuda")
+    engine.fp12_product_dev(d_in, n, scratch, d_out, stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint64), gt_prod)
+
+
 def test_full_size_final_exp_config2_properties(engine, coracle, pyref):
     """BASELINE config[2] shape (final exponentiation only) at 2^16 here: outputs lie in the order-r
     subgroup (checked on a sample via the oracle) and f -> f^2 commutes with the map."""
