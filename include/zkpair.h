@@ -232,6 +232,16 @@ int32_t zkp_g1_mul_batch(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_
 int32_t zkp_g2_mul_batch(zkp_ctx *ctx, const uint64_t *g2_xy, const uint8_t *g2_inf, const uint64_t *scalars,
                          size_t n, uint64_t *out_xy, uint8_t *out_inf);
 
+/* `&G1Affine + &G1Affine` (src/g1.rs:155-187, double() :74-91) and `&G2Affine + &G2Affine` (src/g2.rs:210-242,
+ * :81-105): the affine chord-and-tangent law, element-wise a[i] + b[i].  An identity operand passes the other one
+ * through, equal points double.  out_flag[i]: bit0 = the sum is the identity (0, 1); bit1 = the reference divides
+ * by zero and panics here (P + (-P) src/g1.rs:177, or doubling a point with y = 0) -- the identity is returned.
+ * `a - b` is a + (-b) with -b = (x, p - y) (src/g1.rs:118-128): negate on the host or with ZKP_OP_FP_NEG. */
+int32_t zkp_g1_add_batch(zkp_ctx *ctx, const uint64_t *a_xy, const uint8_t *a_inf, const uint64_t *b_xy, const uint8_t *b_inf,
+                         size_t n, uint64_t *out_xy, uint8_t *out_flag);
+int32_t zkp_g2_add_batch(zkp_ctx *ctx, const uint64_t *a_xy, const uint8_t *a_inf, const uint64_t *b_xy, const uint8_t *b_inf,
+                         size_t n, uint64_t *out_xy, uint8_t *out_flag);
+
 /* ---- measurement helpers -------------------------------------------------------------------- */
 
 /* Integer-multiply roofline probe: runs independent IMAD.WIDE.U32 (kind 0), IMAD lo (kind 1) or

@@ -16,7 +16,8 @@
  *   Fp12 (src/fp12.rs:13, methods :75-210)              zkp::Fp12    mul_by_014 conjugate frobenius_map pow_vartime ...
  *   From<Fp> for Fp2/Fp6/Fp12 (replicating, src/fp2.rs:32-36, src/fp6.rs:19-27, src/fp12.rs:18-25)   T::from(...)
  *   G1Affine / G2Affine (src/g1.rs:7-62, src/g2.rs:8-69) zkp::G1Affine / G2Affine: identity generator is_identity
- *                                                                    is_valid is_on_curve is_torsion_free neg, * Fr limbs
+ *                                                                    is_valid is_on_curve is_torsion_free neg double_
+ *                                                                    + - (affine law), * Fr limbs
  *   pairings::* (src/pairings.rs is EMPTY)    zkp::pairings::{pairing, miller_loop, multi_miller_loop,
  *                                                                    final_exponentiation, pairing_batch, multi_pairing_batch}
  *
@@ -358,13 +359,24 @@ struct G1Affine {
         out.is_infinity = oinf != 0;
         return out;
     }
-    G1Affine double_() const { return mul(fr_from(2)); }                                      /* `double`, src/g1.rs:64-92 */
+    /* `&G1Affine + &G1Affine` (src/g1.rs:155-187); P + (-P) divides by zero in the crate and panics (:177) */
+    G1Affine add(const G1Affine &o) const {
+        G1Affine out;
+        uint8_t ia = is_infinity, ib = o.is_infinity, flag = 0;
+        Engine::check(zkp_g1_add_batch(Engine::ctx(), x.v, &ia, o.x.v, &ib, 1, out.x.v, &flag));
+        if (flag & 2) throw Panic("called `Option::unwrap()` on a `None` value (affine addition: division by zero)");
+        out.is_infinity = (flag & 1) != 0;
+        return out;
+    }
+    G1Affine double_() const { return is_infinity ? identity() : add(*this); }                /* `double`, src/g1.rs:74-91 */
 };
 /* points compare by coordinates only: is_infinity is ignored (src/g1.rs:13-17) */
 inline bool operator==(const G1Affine &a, const G1Affine &b) { return a.x == b.x && a.y == b.y; }
 inline bool operator!=(const G1Affine &a, const G1Affine &b) { return !(a == b); }
 inline G1Affine operator-(const G1Affine &a) { return a.neg(); }
 inline G1Affine operator*(const G1Affine &a, const FrLimbs &k) { return a.mul(k); }
+inline G1Affine operator+(const G1Affine &a, const G1Affine &b) { return a.add(b); }
+inline G1Affine operator-(const G1Affine &a, const G1Affine &b) { return a.add(b.neg()); }            /* src/g1.rs:189-196 */
 
 /* ---- G2Affine (src/g2.rs) ------------------------------------------------------------------ */
 struct G2Affine {
@@ -411,12 +423,23 @@ struct G2Affine {
         out.is_infinity = oinf != 0;
         return out;
     }
-    G2Affine double_() const { return mul(fr_from(2)); }                                      /* `double`, src/g2.rs:81-107 */
+    /* `&G2Affine + &G2Affine` (src/g2.rs:210-242); P + (-P) panics in the crate (:232) */
+    G2Affine add(const G2Affine &o) const {
+        G2Affine out;
+        uint8_t ia = is_infinity, ib = o.is_infinity, flag = 0;
+        Engine::check(zkp_g2_add_batch(Engine::ctx(), x.c0.v, &ia, o.x.c0.v, &ib, 1, out.x.c0.v, &flag));
+        if (flag & 2) throw Panic("called `Option::unwrap()` on a `None` value (affine addition: division by zero)");
+        out.is_infinity = (flag & 1) != 0;
+        return out;
+    }
+    G2Affine double_() const { return is_infinity ? identity() : add(*this); }                /* `double`, src/g2.rs:81-105 */
 };
 inline bool operator==(const G2Affine &a, const G2Affine &b) { return a.x == b.x && a.y == b.y; } /* src/g2.rs:14-18 */
 inline bool operator!=(const G2Affine &a, const G2Affine &b) { return !(a == b); }
 inline G2Affine operator-(const G2Affine &a) { return a.neg(); }
 inline G2Affine operator*(const G2Affine &a, const FrLimbs &k) { return a.mul(k); }
+inline G2Affine operator+(const G2Affine &a, const G2Affine &b) { return a.add(b); }
+inline G2Affine operator-(const G2Affine &a, const G2Affine &b) { return a.add(b.neg()); }            /* src/g2.rs:244-251 */
 
 static_assert(offsetof(G1Affine, y) == 48 && offsetof(G2Affine, y) == 96, "x|y must be contiguous for the C ABI");
 

@@ -229,6 +229,24 @@ static void test_g1() {
     ASSERT_EQ((g * fr_from(5)) * fr_from(7), g * fr_from(35));
     ASSERT_EQ(-(g * fr_from(3)), (-g) * fr_from(3));
     ASSERT((g * KAT_R).is_identity());  // r * G = identity
+    // `&G1Affine + &G1Affine` (src/g1.rs:155-187): identity laws, tangent = double, repeated addition = scalar multiple
+    ASSERT_EQ(G1Affine::identity() + g, g);
+    ASSERT_EQ(g + G1Affine::identity(), g);
+    ASSERT((G1Affine::identity() + G1Affine::identity()).is_identity());
+    ASSERT_EQ(g + g, g.double_());
+    {
+        G1Affine acc = G1Affine::identity();
+        for (int i = 0; i < 9; ++i) acc = acc + g;
+        ASSERT_EQ(acc, g * fr_from(9));
+        ASSERT_EQ(acc - g, g * fr_from(8));
+        bool panicked = false;          // P + (-P): the crate's slope division unwraps None
+        try {
+            (void)(g + (-g));
+        } catch (const Panic &) {
+            panicked = true;
+        }
+        ASSERT(panicked);
+    }
     G1Affine off = G1Affine::new_(g.x, g.x, false);
     ASSERT_EQ(off.is_valid().err, std::string("Point is not on curve"));
     ASSERT(!off.is_on_curve());
@@ -244,6 +262,23 @@ static void test_g2() {
     for (int i = 0; i < 5; ++i) {                                                       // test_scalar_multiplication
         uint64_t r = rng() % 100, s = rng() % 100;
         ASSERT_EQ((g * fr_from(r)) * fr_from(s), g * fr_from(r * s));
+    }
+    {   // ... as the crate writes it: lhs = &a * &k, rhs = (0..r).fold(identity, |acc, _| acc + &a)
+        uint64_t r = 2 + rng() % 20;
+        G2Affine a = g * fr_from(1 + rng() % 1000);
+        G2Affine rhs = G2Affine::identity();
+        for (uint64_t i = 0; i < r; ++i) rhs = rhs + a;
+        ASSERT_EQ(a * fr_from(r), rhs);
+    }
+    {   // test_affine_addition: identity + identity, identity + generator, generator + generator = double
+        G2Affine c = G2Affine::identity() + G2Affine::identity();
+        ASSERT(c.is_identity());
+        ASSERT(c.is_valid().is_ok());
+        ASSERT_EQ(G2Affine::identity() + g, g);
+        ASSERT_EQ(g + G2Affine::identity(), g);
+        ASSERT_EQ(g + g, g_double);
+        ASSERT_EQ((g + g) - g, g);
+        ASSERT((g + g_double).is_valid().is_ok());
     }
     ASSERT((g * fr_from(0)).is_identity());
     ASSERT((g * KAT_R).is_identity());

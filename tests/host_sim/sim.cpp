@@ -141,6 +141,21 @@ int sim_group_op(int gop, const uint64_t *pts, const uint8_t *inf, const uint64_
     });
     return anybad.load() ? -1 : 0;
 }
+// element-wise affine addition (gop 4 = G1, 5 = G2): out = a + b, flag bit0 identity, bit1 undefined in the reference
+int sim_group_add(int gop, const uint64_t *a, const uint8_t *ainf, const uint64_t *b, const uint8_t *binf, uint64_t *out, uint8_t *flag, size_t n) {
+    std::atomic<int> anybad{0};
+    const int w = (gop & 1) ? 24 : 12;
+    run_pair([&]() {
+        for (size_t i = 0; i < n; i++) {
+            bool bad = false;
+            uint8_t ia = ainf ? ainf[i] : 0, ib = binf ? binf[i] : 0;
+            if (gop == GOP_G1_ADD) g1_add_one(a + w * i, ia, b + w * i, ib, out + w * i, flag + i, bad);
+            else g2_add_one(a + w * i, ia, b + w * i, ib, out + w * i, flag + i, bad);
+            if (lane_or(bad)) anybad.store(1);
+        }
+    });
+    return anybad.load() ? -1 : 0;
+}
 // Montgomery-trick batch inversion of pairing.cuh (one simulated thread, runs of `run` elements)
 void sim_batch_inv(const uint64_t *in, uint64_t *out, size_t n, int run) {
     zkp_sim_par = 0;

@@ -380,6 +380,27 @@ def test_group_scalar_mul_matches_oracle(engine, coracle):
     assert np.array_equal(gt1, gt2)
 
 
+def test_group_addition_matches_oracle(engine, coracle):
+    """zkp_g1_add_batch / zkp_g2_add_batch: every branch of the reference's affine law, and [2]P + P == [3]P
+    against the scalar-multiplication kernel on a larger batch."""
+    for group, add, (a, ai, b, bi) in zip(("g1", "g2"), (engine.g1_add_batch, engine.g2_add_batch), util.group_add_cases(coracle)):
+        out, flag = add(a, b, ai, bi)
+        exp, einf, pan = util.oracle_group_add(coracle, group, a, ai, b, bi)
+        assert np.array_equal(flag & 1, einf) and np.array_equal((flag & 2) != 0, pan)
+        assert np.array_equal(out[einf == 0], exp[einf == 0])
+    n = 777
+    g1, _, g2, _ = engine.gen_points(0x3A, 0, n)
+    two, three = np.zeros((n, 4), np.uint64), np.zeros((n, 4), np.uint64)
+    two[:, 0], three[:, 0] = 2, 3
+    for pts, mul, add in ((g1, engine.g1_mul_batch, engine.g1_add_batch), (g2, engine.g2_mul_batch, engine.g2_add_batch)):
+        dbl, _ = mul(pts, two)
+        tri, _ = mul(pts, three)
+        s, flag = add(dbl, pts)
+        assert not flag.any() and np.array_equal(s, tri)
+        d2, flag = add(pts, pts)                      # the tangent branch
+        assert not flag.any() and np.array_equal(d2, dbl)
+
+
 def test_imad_peak_probe(engine):
     wide = engine.imad_peak(0)
     lo = engine.imad_peak(1)

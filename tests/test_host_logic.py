@@ -256,6 +256,20 @@ def test_sim_prepared_g2_tables(sim, coracle):
     assert np.array_equal(out2, exp2)
 
 
+def test_sim_group_addition(sim, coracle):
+    """`&G1Affine + &G1Affine` / `&G2Affine + &G2Affine` (src/g1.rs:155-187, src/g2.rs:210-242): every branch of the
+    affine law in the device code vs the oracle; P + (-P), where the reference panics, is flagged."""
+    for gop, group, (a, ai, b, bi) in zip((4, 5), ("g1", "g2"), util.group_add_cases(coracle)):
+        n, w = a.shape
+        out, flag = np.zeros((n, w), np.uint64), np.full(n, 9, np.uint8)
+        assert sim.sim_group_add(gop, _p(a), _p(ai), _p(b), _p(bi), _p(out), _p(flag), ctypes.c_size_t(n)) == 0
+        exp, einf, pan = util.oracle_group_add(coracle, group, a, ai, b, bi)
+        assert np.array_equal(flag & 1, einf) and np.array_equal((flag & 2) != 0, pan)
+        keep = einf == 0
+        assert np.array_equal(out[keep], exp[keep])
+        assert pan.sum() == 1 and einf.sum() == 2       # P + (-P) and identity + identity
+
+
 def test_sim_final_exponentiation_edge_inputs(sim, coracle, pyref):
     """The staged final exponentiation (compressed squarings, factorised hard part) on inputs that are not
     Miller-loop outputs -- zero, one, subfield elements (degenerate decompression), random Fp12 -- against the

@@ -212,3 +212,38 @@ def final_exp_edge_inputs(seed=11, n_random=6):
             z[:6] + [1] + z[7:]]                                                    # w
     rows += [[rng.randrange(o.P) for _ in range(12)] for _ in range(n_random)]
     return np.stack([fp_arr(r) for r in rows])
+
+
+def group_add_cases(coracle, n_random=6, seed=0xADD):
+    """(a, a_inf, b, b_inf) rows for G1 and G2 covering every branch of the reference's affine `add`
+    (src/g1.rs:155-187, src/g2.rs:210-242): generic chord, P + P (tangent), P + (-P) (the reference panics),
+    identity + Q, P + identity, identity + identity."""
+    g1, _, g2, _ = oracle_points(coracle, seed, 0, 2 * n_random + 2)
+
+    def build(pts, w):
+        half = w // 2
+        a = [pts[i] for i in range(n_random)]
+        b = [pts[n_random + i] for i in range(n_random)]
+        ai, bi = [0] * n_random, [0] * n_random
+        p = pts[2 * n_random]
+        q = pts[2 * n_random + 1]
+        neg = p.copy()
+        yl = [o.fp_from_u64([int(v) for v in p[half + 6 * k: half + 6 * k + 6]]) for k in range(half // 6)]
+        neg[half:] = fp_arr([(o.P - y) % o.P for y in yl])
+        for x, y, xi, yi in ((p, p, 0, 0), (p, neg, 0, 0), (p, q, 1, 0), (p, q, 0, 1), (p, q, 1, 1)):
+            a.append(x); b.append(y); ai.append(xi); bi.append(yi)
+        return np.stack(a), np.array(ai, np.uint8), np.stack(b), np.array(bi, np.uint8)
+    return build(g1, 12), build(g2, 24)
+
+
+def oracle_group_add(coracle, group, a, ai, b, bi):
+    """Element-wise oracle sums -> (points, identity flags, panics) ; `panics` marks P + (-P)."""
+    w = a.shape[1]
+    out, inf, pan = np.zeros_like(a), np.zeros(len(a), np.uint8), np.zeros(len(a), bool)
+    for j in range(len(a)):
+        if not ai[j] and not bi[j] and np.array_equal(a[j][: w // 2], b[j][: w // 2]) and not np.array_equal(a[j][w // 2:], b[j][w // 2:]):
+            pan[j] = True      # equal x, different y: the reference divides by zero (src/g1.rs:177)
+            inf[j] = 1
+            continue
+        out[j], inf[j] = coracle.group_op(group, "add", a[j], int(ai[j]), b[j], int(bi[j]))
+    return out, inf, pan

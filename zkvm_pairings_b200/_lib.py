@@ -55,6 +55,8 @@ SYMBOLS = {
     "zkp_g2_check_batch": (ctypes.c_int32, [ctypes.c_void_p, c_u64p, c_u8p, ctypes.c_size_t, c_u8p]),
     "zkp_g1_mul_batch": (ctypes.c_int32, [ctypes.c_void_p, c_u64p, c_u8p, c_u64p, ctypes.c_size_t, c_u64p, c_u8p]),
     "zkp_g2_mul_batch": (ctypes.c_int32, [ctypes.c_void_p, c_u64p, c_u8p, c_u64p, ctypes.c_size_t, c_u64p, c_u8p]),
+    "zkp_g1_add_batch": (ctypes.c_int32, [ctypes.c_void_p, c_u64p, c_u8p, c_u64p, c_u8p, ctypes.c_size_t, c_u64p, c_u8p]),
+    "zkp_g2_add_batch": (ctypes.c_int32, [ctypes.c_void_p, c_u64p, c_u8p, c_u64p, c_u8p, ctypes.c_size_t, c_u64p, c_u8p]),
     "zkp_imad_peak": (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]),
     "zkp_launch_count": (ctypes.c_uint64, [ctypes.c_void_p]),
     "zkp_set_kernel_timing": (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_int32]),

@@ -97,10 +97,10 @@ k_g2_prepare(const uint64_t *__restrict__ g2, Fp *__restrict__ out, uint32_t *er
 }
 
 // Group-level batch ops: subgroup/on-curve validation and scalar multiplication.
-// gop = GroupOp; points are 12 (G1) or 24 (G2) u64 each; flag = status (checks) or is_infinity (mul).
+// gop = GroupOp; points are 12 (G1) or 24 (G2) u64 each; flag = status (checks), is_infinity (mul) or bit0 identity | bit1 undefined (add).
 __global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS)
 k_group_op(int gop, const uint64_t *__restrict__ pts, const uint8_t *__restrict__ inf, const uint64_t *__restrict__ scalars,
-           uint64_t *__restrict__ out_pts, uint8_t *__restrict__ flag, uint32_t *err, size_t n) {
+           uint64_t *__restrict__ out_pts, uint8_t *__restrict__ flag, uint32_t *err, size_t n, const uint8_t *__restrict__ inf2) {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     if (i >= n) return;
     const int w = (gop & 1) ? 24 : 12;
@@ -110,7 +110,10 @@ k_group_op(int gop, const uint64_t *__restrict__ pts, const uint8_t *__restrict_
         case GOP_G1_CHECK: f = g1_check_one(pts + (size_t)w * i, is_inf, bad); break;
         case GOP_G2_CHECK: f = g2_check_one(pts + (size_t)w * i, is_inf, bad); break;
         case GOP_G1_MUL: g1_mul_one(pts + (size_t)w * i, is_inf, scalars + 4 * i, out_pts + (size_t)w * i, flag + i, bad); break;
-        default: g2_mul_one(pts + (size_t)w * i, is_inf, scalars + 4 * i, out_pts + (size_t)w * i, flag + i, bad); break;
+        case GOP_G2_MUL: g2_mul_one(pts + (size_t)w * i, is_inf, scalars + 4 * i, out_pts + (size_t)w * i, flag + i, bad); break;
+        // additions: the second operand travels in `scalars` (w u64 per element), its flags in inf2
+        case GOP_G1_ADD: g1_add_one(pts + (size_t)w * i, is_inf, scalars + (size_t)w * i, inf2 ? inf2[i] : 0, out_pts + (size_t)w * i, flag + i, bad); break;
+        default: g2_add_one(pts + (size_t)w * i, is_inf, scalars + (size_t)w * i, inf2 ? inf2[i] : 0, out_pts + (size_t)w * i, flag + i, bad); break;
     }
     bad = lane_or(bad);
     if (lane_par() == 0) {
@@ -653,23 +656,30 @@ static int32_t run_slice(zkp_ctx *ctx, DevState &d, const HostJob &j, size_t lo,
             if (j.flags) CUS(d2h(B_FLAG, j.flags + c0, B[B_FLAG].p, cn));
         } else if (j.mode == 48) {
             const size_t w = (j.op & 1) ? 24 : 12;
-            const bool is_mul = j.op >= GOP_G1_MUL;
+            const bool is_mul = j.op >= GOP_G1_MUL;          // has a second operand and an output point
+            const bool is_add = j.op >= GOP_G1_ADD;
+            const size_t w2 = is_add ? w : 4;                 // u64 per element of the second operand
             CUS(B[B_IN].ensure(cn * w * 8));
             CUS(B[B_FLAG].ensure(cn));
             CUS(h2d(B_IN, B[B_IN].p, j.pts + c0 * w, cn * w * 8));
-            const uint8_t *dinf = nullptr;
+            const uint8_t *dinf = nullptr, *dinf2 = nullptr;
             if (j.g1inf) {
                 CUS(B[B_G1INF].ensure(cn));
                 CUS(h2d(B_G1INF, B[B_G1INF].p, j.g1inf + c0, cn));
                 dinf = (const uint8_t *)B[B_G1INF].p;
             }
+            if (is_add && j.g2inf) {
+                CUS(B[B_G2INF].ensure(cn));
+                CUS(h2d(B_G2INF, B[B_G2INF].p, j.g2inf + c0, cn));
+                dinf2 = (const uint8_t *)B[B_G2INF].p;
+            }
             if (is_mul) {
-                CUS(B[B_G2].ensure(cn * 32));
+                CUS(B[B_G2].ensure(cn * w2 * 8));
                 CUS(B[B_OUT].ensure(cn * w * 8));
-                CUS(h2d(B_G2, B[B_G2].p, j.scalars + c0 * 4, cn * 32));
+                CUS(h2d(B_G2, B[B_G2].p, j.scalars + c0 * w2, cn * w2 * 8));
             }
             k_group_op<<<grid_for(cn), ZKP_TPB, 0, st>>>(j.op, (const uint64_t *)B[B_IN].p, dinf, is_mul ? (const uint64_t *)B[B_G2].p : nullptr,
-                                                        is_mul ? (uint64_t *)B[B_OUT].p : nullptr, (uint8_t *)B[B_FLAG].p, d.d_err, cn);
+                                                        is_mul ? (uint64_t *)B[B_OUT].p : nullptr, (uint8_t *)B[B_FLAG].p, d.d_err, cn, dinf2);
             ctx->launches++;
             CUS(cudaGetLastError());
             if (is_mul) CUS(d2h(B_OUT, j.out + c0 * w, B[B_OUT].p, cn * w * 8));
@@ -940,11 +950,19 @@ int32_t zkp_fp_to_bytes_batch(zkp_ctx *ctx, const uint64_t *limbs, size_t n, uin
 }
 
 static int32_t group_job(zkp_ctx *ctx, int gop, const uint64_t *pts, const uint8_t *inf, const uint64_t *scalars, size_t n,
-                         uint64_t *out, uint8_t *flags) {
+                         uint64_t *out, uint8_t *flags, const uint8_t *inf2 = nullptr) {
     if (n && (!pts || !flags || (gop >= GOP_G1_MUL && (!scalars || !out)))) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
     HostJob j;
-    j.mode = 48; j.op = gop; j.pts = pts; j.g1inf = inf; j.scalars = scalars; j.out = out; j.flags = flags;
+    j.mode = 48; j.op = gop; j.pts = pts; j.g1inf = inf; j.g2inf = inf2; j.scalars = scalars; j.out = out; j.flags = flags;
     return run_host_job(ctx, j, n);
+}
+int32_t zkp_g1_add_batch(zkp_ctx *ctx, const uint64_t *a_xy, const uint8_t *a_inf, const uint64_t *b_xy, const uint8_t *b_inf, size_t n,
+                         uint64_t *out_xy, uint8_t *out_flag) {
+    return group_job(ctx, GOP_G1_ADD, a_xy, a_inf, b_xy, n, out_xy, out_flag, b_inf);
+}
+int32_t zkp_g2_add_batch(zkp_ctx *ctx, const uint64_t *a_xy, const uint8_t *a_inf, const uint64_t *b_xy, const uint8_t *b_inf, size_t n,
+                         uint64_t *out_xy, uint8_t *out_flag) {
+    return group_job(ctx, GOP_G2_ADD, a_xy, a_inf, b_xy, n, out_xy, out_flag, b_inf);
 }
 int32_t zkp_g1_check_batch(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_inf, size_t n, uint8_t *status) {
     return group_job(ctx, GOP_G1_CHECK, g1_xy, g1_inf, nullptr, n, nullptr, status);

@@ -262,7 +262,7 @@ ZKP_HD void gen_g2_one(uint64_t k, uint64_t *xy, uint8_t *inf) {
 
 // ------------------------------------------------------------------ group-level batch ops
 
-enum GroupOp { GOP_G1_CHECK = 0, GOP_G2_CHECK = 1, GOP_G1_MUL = 2, GOP_G2_MUL = 3 };
+enum GroupOp { GOP_G1_CHECK = 0, GOP_G2_CHECK = 1, GOP_G1_MUL = 2, GOP_G2_MUL = 3, GOP_G1_ADD = 4, GOP_G2_ADD = 5 };
 #ifndef ZKP_POINT_OK   /* same values as include/zkpair.h */
 #define ZKP_POINT_OK 0
 #define ZKP_POINT_NOT_ON_CURVE 1
@@ -318,6 +318,58 @@ ZKP_HD void g2_mul_one(const uint64_t *xy, uint8_t inf, const uint64_t *k, uint6
     if (lane_par() == 0) *out_inf = is_inf ? 1 : 0;
     store_fp2(out_xy, ax, nullptr);
     store_fp2(out_xy + 12, ay, nullptr);
+}
+
+// P + Q with the affine chord-and-tangent law of `&G1Affine + &G1Affine` / `&G2Affine + &G2Affine`
+// (src/g1.rs:155-187 with double() :74-91; src/g2.rs:210-242 with :81-105): identity operands pass the
+// other one through, equal points double, slope = (y2 - y1) / (x2 - x1) or 3 x^2 / (2 y).  Where the
+// reference divides by zero and panics (P + (-P), or doubling a point with y = 0) the result is the
+// identity (0, 1) and bit1 of the flag is set.  flag bit0 = the result is the identity.
+template <class O>
+ZKP_HD uint8_t affine_add(typename O::T &xr, typename O::T &yr, const typename O::T &x1, const typename O::T &y1, bool inf1,
+                          const typename O::T &x2, const typename O::T &y2, bool inf2) {
+    typedef typename O::T T;
+    if (inf1 | inf2) {
+        bool both = inf1 & inf2;
+        xr = both ? O::zero() : (inf1 ? x2 : x1);
+        yr = both ? O::one() : (inf1 ? y2 : y1);
+        return both ? 1 : 0;
+    }
+    T dx = O::sub(x2, x1), dy = O::sub(y2, y1), num, den;
+    if (O::is_zero(dx) && O::is_zero(dy)) {
+        T xx = O::sqr(x1);
+        num = O::add(O::add(xx, xx), xx);
+        den = O::add(y1, y1);
+    } else {
+        num = dy;
+        den = dx;
+    }
+    if (O::is_zero(den)) {
+        xr = O::zero();
+        yr = O::one();
+        return 3;
+    }
+    T slope = O::mul(num, O::inv(den));
+    xr = O::sub(O::sub(O::sqr(slope), x1), x2);
+    yr = O::sub(O::mul(slope, O::sub(x1, xr)), y1);
+    return 0;
+}
+ZKP_HD void g1_add_one(const uint64_t *a, uint8_t ainf, const uint64_t *b, uint8_t binf, uint64_t *out_xy, uint8_t *flag, bool &bad) {
+    Fp x1 = load_fp(a, bad), y1 = load_fp(a + 6, bad), x2 = load_fp(b, bad), y2 = load_fp(b + 6, bad), xr, yr;
+    uint8_t f = affine_add<OpsFp>(xr, yr, x1, y1, ainf != 0, x2, y2, binf != 0);
+    if (lane_par() == 0) {
+        *flag = f;
+        store_fp(out_xy, xr, nullptr);
+    } else {
+        store_fp(out_xy + 6, yr, nullptr);
+    }
+}
+ZKP_HD void g2_add_one(const uint64_t *a, uint8_t ainf, const uint64_t *b, uint8_t binf, uint64_t *out_xy, uint8_t *flag, bool &bad) {
+    Fp2 x1 = load_fp2(a, bad), y1 = load_fp2(a + 12, bad), x2 = load_fp2(b, bad), y2 = load_fp2(b + 12, bad), xr, yr;
+    uint8_t f = affine_add<OpsFp2>(xr, yr, x1, y1, ainf != 0, x2, y2, binf != 0);
+    if (lane_par() == 0) *flag = f;
+    store_fp2(out_xy, xr, nullptr);
+    store_fp2(out_xy + 12, yr, nullptr);
 }
 
 }  // namespace zkp

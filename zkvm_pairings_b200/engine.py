@@ -325,6 +325,24 @@ class PairingEngine:
         return self._mul(self._lib.zkp_g2_mul_batch, g2, 24, g2_inf, scalars)
 
     # ------------------------------------------------------------------ device-resident (torch tensors)
+    def _add(self, fn, a, b, width, a_inf, b_inf):
+        a, ai, n = self._pts(a, width, a_inf)
+        b, bi, nb = self._pts(b, width, b_inf)
+        if nb != n:
+            raise ValueError("operands differ in length")
+        out, flag = np.empty((n, width), np.uint64), np.zeros(n, np.uint8)
+        self._check(fn(self._ctx, _ptr(a), _ptr(ai), _ptr(b), _ptr(bi), n, _ptr(out), _ptr(flag)))
+        return out, flag
+
+    def g1_add_batch(self, a, b, a_inf=None, b_inf=None):
+        """a_i + b_i, `&G1Affine + &G1Affine` (src/g1.rs:155-187) -> (points (n,12), flag: bit0 identity, bit1 the
+        reference panics here (P + (-P)): identity returned)."""
+        return self._add(self._lib.zkp_g1_add_batch, a, b, 12, a_inf, b_inf)
+
+    def g2_add_batch(self, a, b, a_inf=None, b_inf=None):
+        """`&G2Affine + &G2Affine` (src/g2.rs:210-242)."""
+        return self._add(self._lib.zkp_g2_add_batch, a, b, 24, a_inf, b_inf)
+
     def pairing_dev(self, mode: int, out, g1=None, g2=None, g1_inf=None, g2_inf=None, in_fp12=None, n_checks=None,
                     pairs_per_check: int = 1, is_one=None, err=None, stream: int = 0, dev: int = 0):
         """Asynchronous launch on device-resident buffers (torch CUDA tensors).  ``stream`` is a raw
