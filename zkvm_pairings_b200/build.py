@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libzkpair.so")
-SOURCES = ["kernels.cu", "pairing_kernel.cu"]
-HEADERS = ["fp.cuh", "tower.cuh", "pairing.cuh", "ops.cuh", "consts.cuh", "../../include/zkpair.h"]
+SOURCES = ["kernels.cu", "pairing_kernel.cu", "fe_kernel.cu"]
+HEADERS = ["fp.cuh", "tower.cuh", "pairing.cuh", "ops.cuh", "fe_scratch.cuh", "consts.cuh", "../../include/zkpair.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -1,0 +1,129 @@
+// Final-exponentiation kernels (k_fe_batch_inv, k_fe_stage) in their own translation unit: like
+// pairing_kernel.cu it is compiled warp-converged, but with its own copy of the device functions so that it
+// can carry its own density of block-wide rendezvous points (ZKP_CODE_SYNC, fp.cuh).  The stage kernels run
+// 3 blocks of 4 warps per SM -- one warp of a block per scheduler -- through ~60 KB of straight-line code
+// against a 32 KB L1.5 instruction cache: keeping the four warps of a block within one Fp6-level body of
+// each other lets them share the fetched lines.  Measured at 2^20 (profiles/r1l_code_sync_variants.txt):
+// no rendezvous 298.0 ms, per compressed squaring 283.3, per Fp6-level body 275.8 (kept), per Fp2 op 278.4.
+#include <cuda_runtime.h>
+
+#define ZKP_CONVERGED 1
+#define zkp zkp_fe
+#ifndef ZKP_FE_SYNC
+#define ZKP_FE_SYNC 4
+#endif
+#define ZKP_LOOP_SYNC ZKP_FE_SYNC
+#include "../../include/zkpair.h"
+#include "fe_scratch.cuh"
+
+#ifndef ZKP_TPB
+#define ZKP_TPB 128           // threads per block
+#endif
+#ifndef ZKP_FE_SPLIT_MIN
+#define ZKP_FE_SPLIT_MIN ((size_t)1 << 15)   // checks; smaller batches run their final exponentiation as one piece
+#endif
+#ifndef ZKP_MIN_BLOCKS_FE
+#define ZKP_MIN_BLOCKS_FE 3   // resident blocks per SM (measured: 2 -> -1.7 %, 4 -> -1.0 %)
+#endif
+
+using namespace zkp;
+
+extern "C" size_t zkp_fe_scratch_bytes(size_t n) { return n * (2 * ZKP_FE_LANE_FP + 1) * sizeof(Fp); }
+
+// norm[i] <- 1 / norm[i]: every thread inverts a run of ZKP_INV_RUN norms with one Fermat ladder
+#ifndef ZKP_INV_RUN
+#define ZKP_INV_RUN 16
+#endif
+__global__ void __launch_bounds__(128) k_fe_batch_inv(Fp *norm, size_t n) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t lo = t * ZKP_INV_RUN;
+    if (lo >= n) return;
+    int cnt = (int)(n - lo < ZKP_INV_RUN ? n - lo : ZKP_INV_RUN);
+    Fp pre[ZKP_INV_RUN];
+    fp_batch_inv(norm + lo, pre, cnt);
+}
+
+// one stage of the final exponentiation (pairing.cuh fe_stage): consumes the inverse the preceding
+// k_fe_batch_inv left in norm[i], leaves the next norm there; the last stage stores the result
+__global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS_FE)
+k_fe_stage(int stage, FeScratch fs, uint64_t *__restrict__ out, uint8_t *__restrict__ is_one, size_t i0, size_t n) {
+    // this launch covers the checks [i0, n) of the batch
+    size_t i = i0 + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1);
+    bool live = i < n;
+    if (!live) i = n - 1;
+    size_t lane = 2 * i + lane_par();
+    FeWork w;
+    Fp12 f;
+    FeState s;
+    if (stage == 0) {
+        fetch_fp12(fs, lane, ZKP_SLOT_F, f);
+        s.c.c0.c = fs.lanes[(size_t)(ZKP_SLOT_FES + 0) * fs.n2 + lane];
+        s.c.c1.c = fs.lanes[(size_t)(ZKP_SLOT_FES + 1) * fs.n2 + lane];
+        s.c.c2.c = fs.lanes[(size_t)(ZKP_SLOT_FES + 2) * fs.n2 + lane];
+        s.t.c = fs.lanes[(size_t)(ZKP_SLOT_FES + 3) * fs.n2 + lane];
+    } else {
+        fetch_cexp(fs, lane, w.c);
+        if (stage == 1 || stage == ZKP_FE_STAGES - 1) fetch_fp12(fs, lane, ZKP_SLOT_M, w.m);
+        if (stage == 2 || stage == 3 || stage == ZKP_FE_STAGES - 1) fetch_fp12(fs, lane, ZKP_SLOT_Y, w.y);
+    }
+    Fp ninv = fs.norm[i];
+    Fp nrm = fe_stage(stage, w, &f, &s, ninv, &f);
+    if (stage == ZKP_FE_STAGES - 1) {
+        bool one = store_fp12(out + 72 * i, f, live);
+        if (is_one && live && lane_par() == 0) is_one[i] = one ? 1 : 0;
+        return;
+    }
+    if (live) {
+        park_cexp(fs, lane, w.c);
+        if (stage == 0) park_fp12(fs, lane, ZKP_SLOT_M, w.m);
+        if (stage >= 1 && stage <= 3) park_fp12(fs, lane, ZKP_SLOT_Y, w.y);
+        if (lane_par() == 0) fs.norm[i] = nrm;
+    }
+}
+
+// The six (batched inversion, stage) launch pairs over the state k_pairing parked in `scratch`.
+cudaError_t zkp_launch_fe_stages(void *scratch, size_t n, uint64_t *out, uint8_t *is_one, cudaStream_t st, int *launches) {
+    FeScratch fs;
+    fs.lanes = (Fp *)scratch;
+    fs.norm = fs.lanes + 2 * n * ZKP_FE_LANE_FP;
+    fs.n2 = 2 * n;
+    dim3 b(ZKP_TPB);
+    {
+        // The batch runs as two halves on two streams: while one half is in its (latency-bound) batched
+        // inversion or in the tail of a stage kernel, the other half's stage kernel keeps the SMs busy.
+        size_t na = n, nb = 0;
+        if (n >= ZKP_FE_SPLIT_MIN) {
+            na = ((n / 2) + 63) & ~(size_t)63;
+            nb = n - na;
+        }
+        cudaStream_t s2 = nullptr;
+        cudaEvent_t fork = nullptr, join = nullptr;
+        if (nb) {
+            cudaError_t e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(fork, st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s2, fork, 0);
+            if (e != cudaSuccess) return e;
+        }
+        dim3 ga((unsigned)((2 * na + ZKP_TPB - 1) / ZKP_TPB)), gb((unsigned)((2 * nb + ZKP_TPB - 1) / ZKP_TPB));
+        size_t ta = (na + ZKP_INV_RUN - 1) / ZKP_INV_RUN, tb = (nb + ZKP_INV_RUN - 1) / ZKP_INV_RUN;
+        for (int stage = 0; stage < ZKP_FE_STAGES; stage++) {
+            k_fe_batch_inv<<<(unsigned)((ta + 127) / 128), 128, 0, st>>>(fs.norm, na);
+            k_fe_stage<<<ga, b, 0, st>>>(stage, fs, out, is_one, 0, na);
+            if (nb) {
+                k_fe_batch_inv<<<(unsigned)((tb + 127) / 128), 128, 0, s2>>>(fs.norm + na, nb);
+                k_fe_stage<<<gb, b, 0, s2>>>(stage, fs, out, is_one, na, n);
+            }
+        }
+        *launches = 2 * ZKP_FE_STAGES * (nb ? 2 : 1);
+        if (nb) {
+            cudaEventRecord(join, s2);
+            cudaStreamWaitEvent(st, join, 0);
+            cudaEventDestroy(fork);
+            cudaEventDestroy(join);
+            cudaStreamDestroy(s2);   // returns at once; the stream's resources go when its work has drained
+        }
+    }
+    return cudaGetLastError();
+}

@@ -16,6 +16,7 @@ struct G2P { Fp2 x, y, z; };      // Jacobian-style projective G2 used by the li
 
 // SURVEY 9.1 doubling_step: 8 Fp2 sqr + 3 Fp2 mul.  co = (c0, c1, c2).  r stays normalized.
 ZKP_NOINLINE void doubling_step(G2P &r, Fp2 *co) {
+    ZKP_CODE_SYNC(4);
     Fp2 t0 = fp2_sqr(r.x);
     Fp2 t1 = fp2_sqr(r.y);
     Fp2 t2 = fp2_sqr(t1);
@@ -40,6 +41,7 @@ ZKP_NOINLINE void doubling_step(G2P &r, Fp2 *co) {
 
 // SURVEY 9.1 addition_step: 8 Fp2 sqr + 7 Fp2 mul.  q normalized; r stays normalized.
 ZKP_NOINLINE void addition_step(G2P &r, const G2A &q, Fp2 *co) {
+    ZKP_CODE_SYNC(4);
     Fp2 zz = fp2_sqr(r.z);
     Fp2 yy = fp2_sqr(q.y);
     Fp2 t0 = fp2_mul(zz, q.x);
@@ -114,6 +116,7 @@ ZKP_HD void miller_loop(Fp12 &f, const G1A *ps, const G2A *qs, const bool *skip,
 #pragma unroll 1
     for (int b = 61; b >= -1; b--) {   // b = -1: the final doubling step, no squaring after it
         bool bit = b >= 0 && ((ZKP_X_HALF >> b) & 1);
+        ZKP_CODE_SYNC(1);
         for (int j = 0; j < kv; j++) {
             doubling_step(rs[j], co);
             ell(f, co, ps[j], skip[j], step == 0 && j == 0);
@@ -124,6 +127,7 @@ ZKP_HD void miller_loop(Fp12 &f, const G1A *ps, const G2A *qs, const bool *skip,
         }
         step++;
         if (bit) {
+            ZKP_CODE_SYNC(2);
             for (int j = 0; j < kv; j++) {
                 addition_step(rs[j], qs[j], co);
                 ell(f, co, ps[j], skip[j]);
@@ -134,6 +138,7 @@ ZKP_HD void miller_loop(Fp12 &f, const G1A *ps, const G2A *qs, const bool *skip,
             }
             step++;
         }
+        ZKP_CODE_SYNC(2);
         if (b >= 0) fp12_sqr(f, f);
     }
     fp12_conj(f, f);
@@ -220,6 +225,7 @@ ZKP_NOINLINE Fp cexp_begin(CExp &c, const Fp12 &f) {
     int k = 0;
 #pragma unroll 1
     for (int i = 1; i <= ZKP_CEXP_RUN; i++) {
+        ZKP_CODE_SYNC(3);
         cyc_sqr_compressed(z);
         if ((ZKP_BLS_X >> i) & 1) {
             for (int j = 0; j < 4; j++) c.s[k][j] = z[j];
@@ -233,6 +239,7 @@ ZKP_NOINLINE Fp cexp_begin(CExp &c, const Fp12 &f) {
 }
 // g <- the full element of a snapshot z = (z2..z5); dinv = 1 / cexp_den(z)
 ZKP_NOINLINE void cexp_decompress(Fp12 &g, const Fp2 *z, const Fp2 &dinv) {
+    ZKP_CODE_SYNC(4);
     Fp2 s4 = fp2_sqr(z[2]);
     Fp2 num_a = fp2_sub(fp2_add(fp2_mul_nr(fp2_sqr(z[3])), fp2_add(fp2_dbl(s4), s4)), fp2_dbl(z[1]));
     bool z2z = fp2_is_zero(z[0]);

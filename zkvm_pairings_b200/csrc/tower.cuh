@@ -100,6 +100,7 @@ ZKP_LIN Fp2 fp2_mul_nr(Fp2 a) {
 // which is a0*b0 - a1*b1 in the even lane and a1*b0 + a0*b1 in the odd lane: three 12-word
 // shuffles (one exchange, two broadcasts), one lane-dependent negation, no selects.
 ZKP_NOINLINE Fp2 fp2_mul(Fp2 a, Fp2 b) {
+    ZKP_CODE_SYNC(5);
     bool odd = lane_par() != 0;
     Fp t = fp_xchg(fp_select(odd, fp_neg(a.c), a.c));
     Fp b0 = fp_bcast<0>(b.c), b1 = fp_bcast<1>(b.c);
@@ -111,6 +112,7 @@ ZKP_NOINLINE Fp2 fp2_mul(Fp2 a, Fp2 b) {
 // x = a0 + partner's a is an uncorrected sum (<= 4p), y is 2p-redundant: x*y <= 8p^2 as mont_mul
 // requires.
 ZKP_NOINLINE Fp2 fp2_sqr(Fp2 a) {
+    ZKP_CODE_SYNC(5);
     bool odd = lane_par() != 0;
     Fp pa = fp_xchg(a.c);
     Fp x = fp_add_lazy(fp_bcast<0>(a.c), pa);
@@ -153,6 +155,7 @@ ZKP_HD void fp6_mul_nr(Fp6 &r, const Fp6 &a) {
 }
 // Karatsuba, 6 Fp2 mul (value-equal to mul_interleaved, src/fp6.rs:188-267); r may alias a or b
 ZKP_NOINLINE void fp6_mul(Fp6 &r, const Fp6 &a, const Fp6 &b) {
+    ZKP_CODE_SYNC(4);
     Fp2 v0 = fp2_mul(a.c0, b.c0);
     Fp2 v1 = fp2_mul(a.c1, b.c1);
     Fp2 v2 = fp2_mul(a.c2, b.c2);
@@ -165,6 +168,7 @@ ZKP_NOINLINE void fp6_mul(Fp6 &r, const Fp6 &a, const Fp6 &b) {
 }
 // src/fp6.rs:274-288 ; r may alias a
 ZKP_NOINLINE void fp6_sqr(Fp6 &r, const Fp6 &a) {
+    ZKP_CODE_SYNC(4);
     Fp2 s0 = fp2_sqr(a.c0);
     Fp2 ab = fp2_mul(a.c0, a.c1);
     Fp2 s1 = fp2_dbl(ab);
@@ -178,6 +182,7 @@ ZKP_NOINLINE void fp6_sqr(Fp6 &r, const Fp6 &a) {
 }
 // a * (0, c1, 0)  -- src/fp6.rs:102-108 ; r may alias a
 ZKP_NOINLINE void fp6_mul_by_1(Fp6 &r, const Fp6 &a, const Fp2 &c1) {
+    ZKP_CODE_SYNC(4);
     Fp2 t0 = fp2_mul_nr(fp2_mul(a.c2, c1));
     Fp2 t1 = fp2_mul(a.c0, c1);
     Fp2 t2 = fp2_mul(a.c1, c1);
@@ -185,6 +190,7 @@ ZKP_NOINLINE void fp6_mul_by_1(Fp6 &r, const Fp6 &a, const Fp2 &c1) {
 }
 // a * (c0, c1, 0)  -- src/fp6.rs:110-125 ; r may alias a
 ZKP_NOINLINE void fp6_mul_by_01(Fp6 &r, const Fp6 &a, const Fp2 &c0, const Fp2 &c1) {
+    ZKP_CODE_SYNC(4);
     Fp2 a_a = fp2_mul(a.c0, c0);
     Fp2 b_b = fp2_mul(a.c1, c1);
     Fp2 t1 = fp2_add(fp2_mul_nr(fp2_mul(a.c2, c1)), a_a);
@@ -301,6 +307,7 @@ ZKP_HD void fp12_inv(Fp12 &r, const Fp12 &a) {
 // Fp12::frobenius_map (src/fp12.rs:143-170) has this shape but inherits wrong Fp6 constants
 // (src/fp6.rs:147-173); this is the mathematically correct map.  r may alias a.
 ZKP_NOINLINE void fp12_frobenius(Fp12 &r, const Fp12 &a, int k) {
+    ZKP_CODE_SYNC(4);
     const Fp2 *src[6] = {&a.c0.c0, &a.c1.c0, &a.c0.c1, &a.c1.c1, &a.c0.c2, &a.c1.c2};
     Fp2 *dst[6] = {&r.c0.c0, &r.c1.c0, &r.c0.c1, &r.c1.c1, &r.c0.c2, &r.c1.c2};
     const uint32_t *tab = ZKP_FROB + (k - 1) * (10 * ZKP_NL);
@@ -332,6 +339,7 @@ ZKP_HD Fp2 cyc_plus(const Fp2 &t, const Fp2 &z) {
     return fp2_add(fp2_dbl(w), t);
 }
 ZKP_NOINLINE void fp12_cyclotomic_sqr(Fp12 &r, const Fp12 &f) {
+    ZKP_CODE_SYNC(4);
     Fp2 t0, t1;
     // (z0, z1) = (c0.c0, c1.c1)
     {
