@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """BASELINE config 5: n = 2^LOG2 (default 2^24) independent pairings sharded in contiguous slices over every
 visible GPU, ONE process, host buffers in and out (zkp_pairing_batch: one host thread + two streams per
-device, 2^17-pairing chunks double-buffered), then the same pairs as one global product with the 576-byte
+device, 2^18-pairing chunks double-buffered), then the same pairs as one global product with the 576-byte
 Fp12 gather (zkp_multi_miller_product).  Checks a strided sample of the Gt outputs bit-for-bit against the
 C oracle and the global product against the product of the per-pair Miller outputs of that sample's slice.
 Usage: python tools/prof_config5.py [LOG2=24] [SAMPLE=256]"""
@@ -24,7 +24,7 @@ eng = z.PairingEngine()            # every visible device
 t0 = time.perf_counter()
 g1, i1, g2, i2 = eng.gen_points(0xC0F165, 0, n)
 print("generated 2^%d point pairs on %d GPU(s) in %.1f s (untimed input synthesis)" % (log2, ndev, time.perf_counter() - t0))
-eng.pairing_batch(g1[: 1 << 17], g2[: 1 << 17])          # warm-up: module load, pools, pinned staging
+eng.pairing_batch(g1[: 1 << 18], g2[: 1 << 18])          # warm-up: module load, pools, pinned staging
 gt = np.empty((n, 72), dtype=np.uint64)
 for rep in range(3):                                     # the first pass also page-faults the 9.7 GB of fresh output
     t0 = time.perf_counter()

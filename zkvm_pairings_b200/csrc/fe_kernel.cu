@@ -16,9 +16,11 @@
 #include "../../include/zkpair.h"
 #include "fe_scratch.cuh"
 
-#ifndef ZKP_TPB
-#define ZKP_TPB 128           // threads per block
+#ifndef ZKP_TPB_FE
+#define ZKP_TPB_FE 128        // threads per block of the stage kernels
 #endif
+#undef ZKP_TPB
+#define ZKP_TPB ZKP_TPB_FE
 #ifndef ZKP_FE_SPLIT_MIN
 #define ZKP_FE_SPLIT_MIN ((size_t)1 << 15)   // checks; smaller batches run their final exponentiation as one piece
 #endif

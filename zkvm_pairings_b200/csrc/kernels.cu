@@ -34,7 +34,7 @@
 #define ZKP_MIN_BLOCKS 2      // resident blocks per SM the register allocator must allow
 #endif
 #ifndef ZKP_CHUNK
-#define ZKP_CHUNK (1u << 17)  // checks per host<->device pipeline chunk
+#define ZKP_CHUNK (1u << 18)  // checks per host<->device pipeline chunk (e2e at 2^20: 1.735 / 1.776 / 1.794 M/s for 2^16 / 2^17 / 2^18)
 #endif
 
 using namespace zkp;

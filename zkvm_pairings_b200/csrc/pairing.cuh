@@ -205,7 +205,9 @@ struct CExp {            // one f^|x| between its two halves
 ZKP_NOINLINE void cyc_sqr_compressed(Fp2 *z) {
     Fp2 t0, t1, t2, t3;
     fp4_square(t0, t1, z[0], z[1]);
+    ZKP_CODE_SYNC(6);
     fp4_square(t2, t3, z[2], z[3]);
+    ZKP_CODE_SYNC(6);
     Fp2 n4 = cyc_minus(t0, z[2]);
     Fp2 n5 = cyc_plus(t1, z[3]);
     t0 = fp2_mul_nr(t3);
