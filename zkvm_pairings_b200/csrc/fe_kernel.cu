@@ -3,8 +3,10 @@
 // can carry its own density of block-wide rendezvous points (ZKP_CODE_SYNC, fp.cuh).  The stage kernels run
 // 3 blocks of 4 warps per SM -- one warp of a block per scheduler -- through ~60 KB of straight-line code
 // against a 32 KB L1.5 instruction cache: keeping the four warps of a block within one Fp6-level body of
-// each other lets them share the fetched lines.  Measured at 2^20 (profiles/r1l_code_sync_variants.txt):
-// no rendezvous 298.0 ms, per compressed squaring 283.3, per Fp6-level body 275.8 (kept), per Fp2 op 278.4.
+// each other lets them share the fetched lines -- and with that, four blocks per SM at 128 registers beat three
+// at 168.  Final exponentiation only, 2^20 (profiles/r1l_code_sync_variants.txt, profiles/r1o_occupancy_variants.txt):
+//   3 blocks/SM: no rendezvous 298.0 ms, per compressed squaring 283.3, per Fp6-level body 275.5, per Fp2 op 278.4
+//   2 blocks/SM 310.9;  4 blocks/SM: Fp6-level 266.0 (kept), Fp2-level 266.4;  5 blocks 271.6;  6 blocks 279.5
 #include <cuda_runtime.h>
 
 #define ZKP_CONVERGED 1
@@ -25,11 +27,12 @@
 #define ZKP_FE_SPLIT_MIN ((size_t)1 << 15)   // checks; smaller batches run their final exponentiation as one piece
 #endif
 #ifndef ZKP_MIN_BLOCKS_FE
-#define ZKP_MIN_BLOCKS_FE 3   // resident blocks per SM (measured: 2 -> -1.7 %, 4 -> -1.0 %)
+#define ZKP_MIN_BLOCKS_FE 4   // resident blocks per SM
 #endif
 
 using namespace zkp;
 
+extern "C" void zkp_fe_geometry(int *tpb, int *blocks, int *sync) { *tpb = ZKP_TPB; *blocks = ZKP_MIN_BLOCKS_FE; *sync = ZKP_FE_SYNC; }
 extern "C" size_t zkp_fe_scratch_bytes(size_t n) { return n * (2 * ZKP_FE_LANE_FP + 1) * sizeof(Fp); }
 
 // norm[i] <- 1 / norm[i]: every thread inverts a run of ZKP_INV_RUN norms with one Fermat ladder

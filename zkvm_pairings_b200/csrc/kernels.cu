@@ -363,9 +363,15 @@ extern "C" {
 
 const char *zkp_last_error(void) { return g_err.c_str(); }
 
+extern "C" void zkp_miller_geometry(int *tpb, int *blocks, int *sync);   // pairing_kernel.cu
+extern "C" void zkp_fe_geometry(int *tpb, int *blocks, int *sync);       // fe_kernel.cu
 const char *zkp_version(void) {
-    static char buf[160];
-    snprintf(buf, sizeof buf, "zkpair 0.2 (sm_100a, 2 lanes/pairing, 12x32 CIOS, tpb=%d, min_blocks=%d, chunk=%u)", ZKP_TPB, ZKP_MIN_BLOCKS, (unsigned)ZKP_CHUNK);
+    static char buf[224];
+    int mt, mb, ms, ft, fb, fs;
+    zkp_miller_geometry(&mt, &mb, &ms);
+    zkp_fe_geometry(&ft, &fb, &fs);
+    snprintf(buf, sizeof buf, "zkpair 0.3 (sm_100a, 2 lanes/pairing, 12x32 CIOS; miller %dx%d/SM sync %d, final exp %dx%d/SM sync %d, chunk=%u)",
+             mt, mb, ms, ft, fb, fs, (unsigned)ZKP_CHUNK);
     return buf;
 }
 

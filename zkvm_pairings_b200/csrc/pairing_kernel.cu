@@ -6,10 +6,14 @@
 
 #define ZKP_CONVERGED 1
 #define zkp zkp_conv   // this unit's own copy of the device functions (kernels.cu holds the pair-masked one)
-// block-wide rendezvous once per Miller-loop iteration (ZKP_CODE_SYNC, fp.cuh): 306.0 ms against 311.7 at 2^20;
-// finer points cost more than they bring here (2 blocks of 4 warps per SM): 307.1 / 310.4 / 317.6 at levels 2 / 4 / 5
+// Block-wide rendezvous points (ZKP_CODE_SYNC, fp.cuh) at the entry of every Fp6-level body, and with them FOUR
+// blocks per SM at 128 registers: once the four warps of a block share their instruction fetches, occupancy pays
+// where it used to lose to instruction-fetch stalls.  Miller loop only, 2^20 (profiles/r1o_occupancy_variants.txt):
+//   2 blocks/SM (244 registers): no points 311.7 ms, once per iteration 305.6, Fp6-level 310.4
+//   3 blocks/SM (168): once per iteration 287.5, Fp6-level 289.1
+//   4 blocks/SM (128): once per iteration 287.1, Fp6-level 280.2 (kept), Fp2-level 286.3;  5 blocks 307.5, 6 blocks 315.9
 #ifndef ZKP_MILLER_SYNC
-#define ZKP_MILLER_SYNC 1
+#define ZKP_MILLER_SYNC 4
 #endif
 #define ZKP_LOOP_SYNC ZKP_MILLER_SYNC
 #include "../../include/zkpair.h"
@@ -22,7 +26,7 @@ cudaError_t zkp_launch_fe_stages(void *scratch, size_t n, uint64_t *out, uint8_t
 #define ZKP_TPB 128           // threads per block
 #endif
 #ifndef ZKP_MIN_BLOCKS
-#define ZKP_MIN_BLOCKS 2      // resident blocks per SM the register allocator must allow (Miller kernel)
+#define ZKP_MIN_BLOCKS 4      // resident blocks per SM the register allocator must allow (Miller kernel)
 #endif
 
 using namespace zkp;
@@ -61,6 +65,8 @@ k_pairing(int mode, const uint64_t *__restrict__ g1, const uint8_t *__restrict__
     }
     if (lane_or(bad) && err && live && lane_par() == 0) atomicOr(err, 1u);
 }
+
+extern "C" void zkp_miller_geometry(int *tpb, int *blocks, int *sync) { *tpb = ZKP_TPB; *blocks = ZKP_MIN_BLOCKS; *sync = ZKP_MILLER_SYNC; }
 
 static int pair_capacity(int k) { return k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : 8; }
 
