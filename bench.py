@@ -294,9 +294,9 @@ def run_ours(args):
             "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T wide-MAC/s",
                          "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of the step's launches in the ncu --set
-                         # full capture of a 2^16 step (profiles/r1n_ncu_summary.txt: 8.73 GB, thread-local frames
+                         # full capture of a 2^16 step (profiles/r1p_ncu_summary.txt: 24.35 GB, register spills and thread-local frames
                          # written back past L2), scaled to this batch
-                         "traffic": 8.73e9 * n / 65536.0,
+                         "traffic": 24.35e9 * n / 65536.0,
                          "kernel": "k_pairing<1> + 2 halves x 6 x (k_fe_batch_inv + k_fe_stage) (one step)", "kernel_ms": per_launch_ms, "algorithmic_macs_per_pairing": MACS_PER_PAIRING,
                          "executed_macs_per_pairing": EXECUTED_MACS_PER_PAIRING,
                          "executed_frac": pairs_per_s_kernel * EXECUTED_MACS_PER_PAIRING / peak,
