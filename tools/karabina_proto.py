@@ -1,4 +1,4 @@
-"""Prototype (big-int, oracle arithmetic) of the compressed cyclotomic squaring used by fe_finish:
+"""Prototype (big-int, oracle arithmetic) of the compressed cyclotomic squaring used by the staged final exponentiation (pairing.cuh cexp_begin / cexp_end):
 B/C-only Granger-Scott squarings, decompression of (z0, z1) from (z2..z5), and the f^|x| chain with three
 decompression points.  Checks every step against oracle/pyref.py's cyclotomic_square / cyclotomic_exp."""
 import os

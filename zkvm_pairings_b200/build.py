@@ -16,7 +16,7 @@ SO = os.path.join(HERE, "libzkpair.so")
 SOURCES = ["kernels.cu", "pairing_kernel.cu", "fe_kernel.cu"]
 HEADERS = ["fp.cuh", "tower.cuh", "pairing.cuh", "ops.cuh", "fe_scratch.cuh", "consts.cuh", "../../include/zkpair.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "--threads", "0"]   # the three units compile in parallel
 
 
 def nvcc_path() -> str:
