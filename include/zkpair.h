@@ -32,11 +32,15 @@
  *   - Inputs with a limb vector >= p are rejected with ZKP_ERR_NONCANONICAL (the reference's neg is
  *     undefined there, src/fp.rs:383-405); outputs are then unspecified.
  *   - Host entry points (no suffix) copy host->device, run, copy device->host, and shard the batch
- *     in contiguous slices over the devices of the context.  *_dev entry points take DEVICE
+ *     in contiguous slices over the devices of the context (one host thread and two streams per device,
+ *     2^18-element chunks double-buffered).  Pinned (page-locked or registered) caller buffers are used in
+ *     place; pageable ones are staged through pinned memory so that copies and kernels still overlap.  *_dev entry points take DEVICE
  *     pointers valid on device `dev` (an index into the context's device list), enqueue on
  *     `stream` (a cudaStream_t, NULL = that device's context stream) and return without
  *     synchronising; their error/status words are device resident.
  *   - Calls on one zkp_ctx are serialised by an internal mutex; distinct contexts are independent.
+ *   - include/zkpair.hpp is a header-only C++17 mirror of the crate's value types (Fp .. Fp12, G1Affine,
+ *     G2Affine, pairings::*) over these entry points.
  */
 #ifndef ZKPAIR_H
 #define ZKPAIR_H
