@@ -7,6 +7,7 @@ import ctypes
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -112,6 +113,17 @@ def sim():
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src[0]])
     return ctypes.CDLL(so)
+
+
+def test_integration_doc_lists_every_entry_point():
+    """INTEGRATION.md section 3 (the Rust `extern "C"` block a maintainer pastes) is the output of
+    tools/gen_rust_ffi.py for the current header: every declared entry point, with its current signature."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_ffi.py")], capture_output=True, text=True, check=True).stdout
+    doc = re.sub(r"\s+", " ", open(os.path.join(ROOT, "INTEGRATION.md")).read())
+    lines = [l.strip() for l in out.splitlines() if l.strip().startswith("pub fn")]
+    assert len(lines) >= 39
+    for l in lines:
+        assert re.sub(r"\s+", " ", l) in doc, l
 
 
 def test_sim_tower_ops_bit_exact(sim, coracle, pyref):
