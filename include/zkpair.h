@@ -36,8 +36,9 @@
  *     2^18-element chunks double-buffered).  Pinned (page-locked or registered) caller buffers are used in
  *     place; pageable ones are staged through pinned memory so that copies and kernels still overlap.  *_dev entry points take DEVICE
  *     pointers valid on device `dev` (an index into the context's device list), enqueue on
- *     `stream` (a cudaStream_t, NULL = that device's context stream) and return without
- *     synchronising; their error/status words are device resident.
+ *     `stream` (a cudaStream_t; NULL = the legacy default stream, as everywhere in CUDA, so the launch is
+ *     ordered after the caller's earlier default-stream work) and return without synchronising; their
+ *     error/status words are device resident.  Every entry point restores the caller's current device.
  *   - Calls on one zkp_ctx are serialised by an internal mutex; distinct contexts are independent.
  *   - include/zkpair.hpp is a header-only C++17 mirror of the crate's value types (Fp .. Fp12, G1Affine,
  *     G2Affine, pairings::*) over these entry points.
@@ -148,9 +149,10 @@ int32_t zkp_multi_miller_loop_batch(zkp_ctx *ctx, const uint64_t *g1_xy, const u
 int32_t zkp_multi_pairing_batch(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_inf,
                                 const uint64_t *g2_xy, const uint8_t *g2_inf, size_t n_checks,
                                 int32_t pairs_per_check, uint64_t *out_gt, uint8_t *out_is_one);
-/* prod_i e(G1[i], G2[i]) for one large product: per-device Miller loops over a contiguous slice,
- * per-device Fp12 partial product, gather of the 576-byte partials to the first device, multiply,
- * ONE final exponentiation.  out_miller_product (optional) receives the un-exponentiated product. */
+/* prod_i e(G1[i], G2[i]) for one large product: per-device shared-accumulator Miller loops (four pairs per
+ * loop) over a contiguous slice, streamed in double-buffered chunks, per-device Fp12 partial product, gather
+ * of the 576-byte partials to the first device, multiply, ONE final exponentiation.  out_miller_product
+ * (optional) receives the un-exponentiated product (a field element: independent of the grouping). */
 int32_t zkp_multi_miller_product(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_inf,
                                  const uint64_t *g2_xy, const uint8_t *g2_inf, size_t n,
                                  uint64_t *out_miller_product, uint64_t *out_gt);

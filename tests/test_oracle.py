@@ -299,3 +299,111 @@ def test_c_oracle_scalar_mul_matches_python(coracle, pyref):
         if not p[2]:
             assert arr_fp(g1[j]) == [p[0], p[1]]
             assert arr_fp(g2[j]) == [q[0][0], q[0][1], q[1][0], q[1][1]]
+
+
+# ---------------------------------------------------------------- definition-level pins of the pairing oracle
+#
+# The reference has no pairing (src/pairings.rs is 0 bytes), so nothing above pins the Miller loop and the
+# final exponentiation except vectors the oracle itself produced.  These tests pin them to the DEFINITION
+# instead, using only the tower arithmetic that the reference's own KATs pin (fp12_mul / fp12_invert /
+# fp12_pow_int): the final exponentiation is a plain power, and the optimal-ate Miller function is recomputed
+# with textbook affine chord-and-tangent lines on the untwisted curve E(Fp12) -- no projective line steps, no
+# sparse products, no Frobenius, no cyclotomic shortcuts.
+
+FE_EXPONENT = None
+
+
+def _fe_exponent(o):
+    global FE_EXPONENT
+    if FE_EXPONENT is None:
+        assert (o.P ** 12 - 1) % o.R_ORDER == 0
+        # the lineage's hard part raises to 3 (p^4 - p^2 + 1) / r (a fixed cofactor of 3, coprime to r)
+        FE_EXPONENT = 3 * (o.P ** 12 - 1) // o.R_ORDER
+    return FE_EXPONENT
+
+
+def _fp12_from_fp(o, a):
+    z = (0, 0)
+    return (((a % o.P, 0), z, z), (z, z, z))
+
+
+def _fp12_from_fp2(o, a):
+    z = (0, 0)
+    return ((a, z, z), (z, z, z))
+
+
+def _textbook_miller(o, p, q):
+    """f_{|x|, Q'}(P) for P in E(Fp), Q' = untwist(Q) in E(Fp12), affine coordinates, vertical lines dropped
+    (they lie in Fp6 and die in the final exponentiation).  Independent of SURVEY 9.1's formulas."""
+    mul, sub, add, inv, sq = o.fp12_mul, o.fp12_sub, o.fp12_add, o.fp12_invert, o.fp12_square
+    z = (0, 0)
+    w = ((z, z, z), ((1, 0), z, z))
+    winv = inv(w)
+    w2i = sq(winv)
+    w3i = mul(w2i, winv)
+    xq = mul(_fp12_from_fp2(o, q[0]), w2i)          # M-type twist: (x', y') -> (x' / w^2, y' / w^3)
+    yq = mul(_fp12_from_fp2(o, q[1]), w3i)
+    four = _fp12_from_fp(o, 4)
+    assert sq(yq) == add(mul(sq(xq), xq), four)      # the untwisted point is on y^2 = x^3 + 4 over Fp12
+    xp, yp = _fp12_from_fp(o, p[0]), _fp12_from_fp(o, p[1])
+    two, three = _fp12_from_fp(o, 2), _fp12_from_fp(o, 3)
+
+    def line_and_step(xt, yt, x2, y2, tangent):
+        lam = mul(mul(three, sq(xt)), inv(mul(two, yt))) if tangent else mul(sub(y2, yt), inv(sub(x2, xt)))
+        l = sub(sub(yp, yt), mul(lam, sub(xp, xt)))
+        x3 = sub(sub(sq(lam), xt), x2)
+        y3 = sub(mul(lam, sub(xt, x3)), yt)
+        return l, x3, y3
+
+    f = o.FP12_ONE
+    xt, yt = xq, yq
+    n = o.X
+    for b in range(n.bit_length() - 2, -1, -1):
+        l, xt, yt = line_and_step(xt, yt, xt, yt, True)
+        f = mul(sq(f), l)
+        if (n >> b) & 1:
+            l, xt, yt = line_and_step(xt, yt, xq, yq, False)
+            f = mul(f, l)
+    return f
+
+
+def test_final_exponentiation_is_the_power_map(pyref, coracle):
+    o = pyref
+    e = _fe_exponent(o)
+    rng = random.Random(2024)
+    ml = o.miller_loop(o.g1_mul(o.G1_GENERATOR, 5), o.g2_mul(o.G2_GENERATOR, 9))
+    rnd = tuple(tuple((rng.randrange(o.P), rng.randrange(o.P)) for _ in range(3)) for _ in range(2))
+    for f in (ml, rnd):
+        want = o.fp12_pow_int(f, e)
+        assert o.final_exponentiation(f) == want
+        # ... and the C oracle (the checker of every GPU parity test) agrees with the definition too
+        assert util.arr_to_fp12(coracle.final_exp_batch(util.fp12_to_arr(f)[None])[0]) == want
+    # the exponent is the full (p^12 - 1)/r up to the cofactor 3: outputs have order dividing r
+    assert o.fp12_pow_int(o.final_exponentiation(rnd), o.R_ORDER) == o.FP12_ONE
+
+
+def test_miller_loop_against_textbook_ate_pairing(pyref, coracle):
+    """pairing(P, Q) == (1 / f_{|x|,Q}(P))^(3 (p^12-1)/r): x is negative, so the optimal-ate Miller function is
+    the inverse of the |x| one; line-scaling conventions differ only by subfield factors, which the final
+    exponentiation kills.  Checked for the generators and for a non-trivial pair."""
+    o = pyref
+    e = _fe_exponent(o)
+    for a, b in ((1, 1), (0xC0FFEE, 0xFACADE)):
+        p, q = o.g1_mul(o.G1_GENERATOR, a), o.g2_mul(o.G2_GENERATOR, b)
+        want = o.fp12_pow_int(o.fp12_invert(_textbook_miller(o, p, q)), e)
+        assert want != o.FP12_ONE                                  # non-degenerate
+        assert o.pairing(p, q) == want
+        got = coracle.pairing_batch(util.g1_to_arr(p)[None], None, util.g2_to_arr(q)[None], None)
+        assert util.arr_to_fp12(got[0]) == want
+    assert o.pairing(o.G1_GENERATOR, o.G2_GENERATOR) == util.hex_fp12(VEC["generators"]["pairing"])
+
+
+def test_pairing_non_degenerate_and_bilinear_in_both_arguments(pyref):
+    o = pyref
+    G1, G2 = o.G1_GENERATOR, o.G2_GENERATOR
+    e = o.pairing(G1, G2)
+    assert e != o.FP12_ONE and o.fp12_pow_int(e, o.R_ORDER) == o.FP12_ONE
+    # r is prime and e != 1, so e generates the order-r subgroup: e^k == 1 only for r | k
+    assert o.fp12_pow_int(e, o.R_ORDER - 1) != o.FP12_ONE
+    assert o.pairing(o.g1_mul(G1, 6), G2) == o.fp12_pow_int(e, 6) == o.pairing(G1, o.g2_mul(G2, 6))
+    assert o.pairing(o.g1_neg(G1), G2) == o.fp12_conjugate(e) == o.fp12_invert(e)

@@ -87,48 +87,45 @@ k_fe_stage(int stage, FeScratch fs, uint64_t *__restrict__ out, uint8_t *__restr
 }
 
 // The six (batched inversion, stage) launch pairs over the state k_pairing parked in `scratch`.
-cudaError_t zkp_launch_fe_stages(void *scratch, size_t n, uint64_t *out, uint8_t *is_one, cudaStream_t st, int *launches) {
+// `aux` = the helper stream and the fork/join events of the two-stream split (owned by the context, created
+// once in zkp_ctx_create; NULL members = run as one piece).
+cudaError_t zkp_launch_fe_stages(void *scratch, size_t n, uint64_t *out, uint8_t *is_one, cudaStream_t st, const ZkpFeAux *aux,
+                                 int *launches) {
     FeScratch fs;
     fs.lanes = (Fp *)scratch;
     fs.norm = fs.lanes + 2 * n * ZKP_FE_LANE_FP;
     fs.n2 = 2 * n;
     dim3 b(ZKP_TPB);
-    {
-        // The batch runs as two halves on two streams: while one half is in its (latency-bound) batched
-        // inversion or in the tail of a stage kernel, the other half's stage kernel keeps the SMs busy.
-        size_t na = n, nb = 0;
-        if (n >= ZKP_FE_SPLIT_MIN) {
-            na = ((n / 2) + 63) & ~(size_t)63;
-            nb = n - na;
-        }
-        cudaStream_t s2 = nullptr;
-        cudaEvent_t fork = nullptr, join = nullptr;
+    // The batch runs as two halves on two streams: while one half is in its (latency-bound) batched
+    // inversion or in the tail of a stage kernel, the other half's stage kernel keeps the SMs busy.
+    size_t na = n, nb = 0;
+    if (n >= ZKP_FE_SPLIT_MIN && aux && aux->s2 && aux->fork && aux->join) {
+        na = ((n / 2) + 63) & ~(size_t)63;
+        nb = n - na;
+    }
+    *launches = 0;
+    cudaStream_t s2 = nb ? aux->s2 : nullptr;
+    if (nb) {
+        cudaError_t e = cudaEventRecord(aux->fork, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s2, aux->fork, 0);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 ga((unsigned)((2 * na + ZKP_TPB - 1) / ZKP_TPB)), gb((unsigned)((2 * nb + ZKP_TPB - 1) / ZKP_TPB));
+    size_t ta = (na + ZKP_INV_RUN - 1) / ZKP_INV_RUN, tb = (nb + ZKP_INV_RUN - 1) / ZKP_INV_RUN;
+    for (int stage = 0; stage < ZKP_FE_STAGES; stage++) {
+        k_fe_batch_inv<<<(unsigned)((ta + 127) / 128), 128, 0, st>>>(fs.norm, na);
+        k_fe_stage<<<ga, b, 0, st>>>(stage, fs, out, is_one, 0, na);
         if (nb) {
-            cudaError_t e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaEventRecord(fork, st);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(s2, fork, 0);
-            if (e != cudaSuccess) return e;
-        }
-        dim3 ga((unsigned)((2 * na + ZKP_TPB - 1) / ZKP_TPB)), gb((unsigned)((2 * nb + ZKP_TPB - 1) / ZKP_TPB));
-        size_t ta = (na + ZKP_INV_RUN - 1) / ZKP_INV_RUN, tb = (nb + ZKP_INV_RUN - 1) / ZKP_INV_RUN;
-        for (int stage = 0; stage < ZKP_FE_STAGES; stage++) {
-            k_fe_batch_inv<<<(unsigned)((ta + 127) / 128), 128, 0, st>>>(fs.norm, na);
-            k_fe_stage<<<ga, b, 0, st>>>(stage, fs, out, is_one, 0, na);
-            if (nb) {
-                k_fe_batch_inv<<<(unsigned)((tb + 127) / 128), 128, 0, s2>>>(fs.norm + na, nb);
-                k_fe_stage<<<gb, b, 0, s2>>>(stage, fs, out, is_one, na, n);
-            }
-        }
-        *launches = 2 * ZKP_FE_STAGES * (nb ? 2 : 1);
-        if (nb) {
-            cudaEventRecord(join, s2);
-            cudaStreamWaitEvent(st, join, 0);
-            cudaEventDestroy(fork);
-            cudaEventDestroy(join);
-            cudaStreamDestroy(s2);   // returns at once; the stream's resources go when its work has drained
+            k_fe_batch_inv<<<(unsigned)((tb + 127) / 128), 128, 0, s2>>>(fs.norm + na, nb);
+            k_fe_stage<<<gb, b, 0, s2>>>(stage, fs, out, is_one, na, n);
         }
     }
-    return cudaGetLastError();
+    *launches = 2 * ZKP_FE_STAGES * (nb ? 2 : 1);
+    cudaError_t rc = cudaGetLastError();
+    if (nb) {   // always rejoin, also after a failed launch: `st` must not run ahead of the helper stream
+        cudaError_t e = cudaEventRecord(aux->join, s2);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, aux->join, 0);
+        if (rc == cudaSuccess) rc = e;
+    }
+    return rc;
 }

@@ -4,6 +4,16 @@
 #pragma once
 #include "ops.cuh"
 
+// helper stream + fork/join events of the final exponentiation's two-stream split; one per context stream,
+// created once in zkp_ctx_create (kernels.cu) so that no call creates or destroys CUDA objects
+#ifndef ZKP_FE_AUX_DEFINED
+#define ZKP_FE_AUX_DEFINED
+struct ZkpFeAux {
+    cudaStream_t s2;
+    cudaEvent_t fork, join;
+};
+#endif
+
 namespace zkp {
 
 // // The final exponentiation is 13 launches: k_pairing (Miller loop and/or load, then fe_prepare), then for

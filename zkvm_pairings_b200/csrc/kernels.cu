@@ -25,13 +25,16 @@
 #include <vector>
 
 #include "../../include/zkpair.h"
-#include "ops.cuh"
+#include "fe_scratch.cuh"   // ops.cuh + the context-owned helper objects of the final exponentiation
 
 #ifndef ZKP_TPB
 #define ZKP_TPB 128           // threads per block of the pairing kernels
 #endif
 #ifndef ZKP_MIN_BLOCKS
 #define ZKP_MIN_BLOCKS 2      // resident blocks per SM the register allocator must allow
+#endif
+#ifndef ZKP_PRODUCT_GROUP
+#define ZKP_PRODUCT_GROUP 4   // pairs per shared-accumulator Miller loop in zkp_multi_miller_product (k_pairing<4>)
 #endif
 #ifndef ZKP_CHUNK
 #define ZKP_CHUNK (1u << 18)  // checks per host<->device pipeline chunk (e2e at 2^20: 1.735 / 1.776 / 1.794 M/s for 2^16 / 2^17 / 2^18)
@@ -276,6 +279,9 @@ struct DevState {
     int id = 0;
     int sms = 0;
     cudaStream_t stream[2] = {nullptr, nullptr};
+    // helper stream + fork/join events of the final exponentiation's two-stream split: one set per context
+    // stream and a third for launches on caller streams (created once here, never in a call)
+    ZkpFeAux fe_aux[3] = {};
     uint32_t *d_err = nullptr;
     cudaMemPool_t pool = nullptr;   // stream-ordered scratch of the final exponentiation (kept, never trimmed)
     DevBuf buf[2][B_NBUF];     // double-buffered pipeline scratch
@@ -294,6 +300,23 @@ struct zkp_ctx {
     bool timing = false;
 };
 
+// Entry points select the device they work on; the caller's current device is restored on every exit path
+// (a torch process keeps allocating on ITS device after a call into a multi-device context).
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();
+            prev = -1;
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 // two threads (one lane pair) per element
 static inline unsigned grid_for(size_t n) { return (unsigned)((2 * n + ZKP_TPB - 1) / ZKP_TPB); }
 
@@ -301,7 +324,8 @@ static inline unsigned grid_for(size_t n) { return (unsigned)((2 * n + ZKP_TPB -
 extern "C" size_t zkp_fe_scratch_bytes(size_t n);
 cudaError_t zkp_launch_k_pairing(int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
                                  size_t n, int k, const uint64_t *in12, uint64_t *out, uint8_t *is_one, uint32_t *err,
-                                 void *scratch, const void *tab, const uint8_t *tabinf, int kf, cudaStream_t st, int *launches);
+                                 void *scratch, const void *tab, const uint8_t *tabinf, int kf, cudaStream_t st, const ZkpFeAux *aux,
+                                 int *launches);
 
 static cudaError_t launch_pairing(zkp_ctx *ctx, DevState &d, int mode, const uint64_t *g1, const uint8_t *g1inf,
                                   const uint64_t *g2, const uint8_t *g2inf, size_t n, int k, const uint64_t *in12,
@@ -321,7 +345,8 @@ static cudaError_t launch_pairing(zkp_ctx *ctx, DevState &d, int mode, const uin
         if (e != cudaSuccess) return e;
     }
     int nl = 0;
-    cudaError_t rc = zkp_launch_k_pairing(mode, g1, g1inf, g2, g2inf, n, k, in12, out, is_one, err, scratch, tab, tabinf, kf, st, &nl);
+    const ZkpFeAux *aux = &d.fe_aux[st == d.stream[0] ? 0 : st == d.stream[1] ? 1 : 2];
+    cudaError_t rc = zkp_launch_k_pairing(mode, g1, g1inf, g2, g2inf, n, k, in12, out, is_one, err, scratch, tab, tabinf, kf, st, aux, &nl);
     ctx->launches += nl;
     if (scratch) cudaFreeAsync(scratch, st);
     if (ctx->timing) {
@@ -398,6 +423,7 @@ int32_t zkp_ctx_create(const int *devices, int n_devices, zkp_ctx **out) {
             ids.push_back(devices[i]);
         }
     }
+    DeviceGuard guard;
     zkp_ctx *c = new zkp_ctx();
     c->devs.resize(ids.size());
     for (size_t i = 0; i < ids.size(); i++) {
@@ -406,6 +432,11 @@ int32_t zkp_ctx_create(const int *devices, int n_devices, zkp_ctx **out) {
         cudaError_t e = cudaSetDevice(d.id);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream[0], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream[1], cudaStreamNonBlocking);
+        for (int a = 0; a < 3 && e == cudaSuccess; a++) {
+            e = cudaStreamCreateWithFlags(&d.fe_aux[a].s2, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.fe_aux[a].fork, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.fe_aux[a].join, cudaEventDisableTiming);
+        }
         if (e == cudaSuccess) e = cudaMalloc(&d.d_err, 4 * sizeof(uint32_t));   // [0] error flag, [1] zero word read by the probes
         if (e == cudaSuccess) e = cudaMemset(d.d_err, 0, 4 * sizeof(uint32_t));
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, d.id);
@@ -433,8 +464,15 @@ int32_t zkp_ctx_create(const int *devices, int n_devices, zkp_ctx **out) {
 
 void zkp_ctx_destroy(zkp_ctx *ctx) {
     if (!ctx) return;
+    DeviceGuard guard;
     for (DevState &d : ctx->devs) {
         cudaSetDevice(d.id);
+        cudaDeviceSynchronize();
+        for (int a = 0; a < 3; a++) {
+            if (d.fe_aux[a].fork) cudaEventDestroy(d.fe_aux[a].fork);
+            if (d.fe_aux[a].join) cudaEventDestroy(d.fe_aux[a].join);
+            if (d.fe_aux[a].s2) cudaStreamDestroy(d.fe_aux[a].s2);
+        }
         for (auto &t : d.timers) {
             cudaEventDestroy(t.first);
             cudaEventDestroy(t.second);
@@ -472,6 +510,7 @@ int32_t zkp_last_kernel_ms(zkp_ctx *ctx, int32_t dev, double *total_ms, uint64_t
     if (!ctx || dev < 0 || dev >= (int)ctx->devs.size()) return fail(ZKP_ERR_INVALID_ARG, "bad ctx/dev");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState &d = ctx->devs[dev];
+    DeviceGuard guard;
     CU(cudaSetDevice(d.id));
     for (auto &t : d.timers) {
         CU(cudaEventSynchronize(t.second));
@@ -509,8 +548,9 @@ int32_t zkp_pairing_dev(zkp_ctx *ctx, int32_t dev, int32_t mode, const uint64_t 
     if (pairs_per_check > ZKP_MAX_PAIRS_PER_CHECK) return fail(ZKP_ERR_TOO_MANY_PAIRS, "pairs_per_check > 8");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState &d = ctx->devs[dev];
+    DeviceGuard guard;
     CU(cudaSetDevice(d.id));
-    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream (CUDA convention)
     CU(launch_pairing(ctx, d, mode, d_g1_xy, d_g1_inf, d_g2_xy, d_g2_inf, n_checks, (mode & 1) ? pairs_per_check : 1,
                       d_in_fp12, d_out, d_is_one, d_err, st));
     return ZKP_OK;
@@ -525,8 +565,9 @@ int32_t zkp_tower_op_dev(zkp_ctx *ctx, int32_t dev, int32_t op, const uint64_t *
     if (!d_a || !d_out || (nb && !d_b)) return fail(ZKP_ERR_INVALID_ARG, "NULL operand");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState &d = ctx->devs[dev];
+    DeviceGuard guard;
     CU(cudaSetDevice(d.id));
-    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream (CUDA convention)
     if (n) {
         k_tower_op<<<grid_for(n), ZKP_TPB, 0, st>>>(op, d_a, d_b, d_out, d_status, d_err, n);
         ctx->launches++;
@@ -542,8 +583,9 @@ int32_t zkp_fp12_product_dev(zkp_ctx *ctx, int32_t dev, const uint64_t *d_in, si
     if (!d_in || !d_out || !d_scratch || n == 0) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer or n == 0");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState &d = ctx->devs[dev];
+    DeviceGuard guard;
     CU(cudaSetDevice(d.id));
-    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream (CUDA convention)
     CU(launch_product(ctx, d_in, n, d_scratch, d_out, d_err, st));
     return ZKP_OK;
 }
@@ -555,8 +597,9 @@ int32_t zkp_gen_points_dev(zkp_ctx *ctx, int32_t dev, uint64_t seed, uint64_t fi
     if (!d_g1_xy || !d_g1_inf || !d_g2_xy || !d_g2_inf) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState &d = ctx->devs[dev];
+    DeviceGuard guard;
     CU(cudaSetDevice(d.id));
-    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream (CUDA convention)
     if (n) {
         k_gen_points<<<grid_for(n), ZKP_TPB, 0, st>>>(seed, first, n, d_g1_xy, d_g1_inf, d_g2_xy, d_g2_inf);
         ctx->launches++;
@@ -574,7 +617,7 @@ static void slice_of(size_t n, size_t ndev, size_t d, size_t &lo, size_t &hi) {
 }
 
 struct HostJob {
-    int mode = 0;   // 1 miller, 2 final exp, 3 pairing ; 16 = tower op ; 32 = gen points ; 48 = group op
+    int mode = 0;   // 1 miller, 2 final exp, 3 pairing ; 16 = tower op ; 32 = gen points ; 48 = group op ; 64 = Miller product
     const uint64_t *pts = nullptr, *scalars = nullptr;   // group op inputs (inf in g1inf, outputs in out / flags)
     const uint64_t *tab = nullptr;                       // prepared G2 line tables shared by all checks (kf of them)
     const uint8_t *tabinf = nullptr;
@@ -597,6 +640,7 @@ static int32_t run_slice(zkp_ctx *ctx, DevState &d, const HostJob &j, size_t lo,
             return ZKP_ERR_CUDA;                                                      \
         }                                                                             \
     } while (0)
+    DeviceGuard guard;
     CUS(cudaSetDevice(d.id));
     CUS(cudaMemsetAsync(d.d_err, 0, sizeof(uint32_t), d.stream[0]));
     CUS(cudaStreamSynchronize(d.stream[0]));
@@ -607,6 +651,7 @@ static int32_t run_slice(zkp_ctx *ctx, DevState &d, const HostJob &j, size_t lo,
     cudaStream_t st = nullptr;
     d.pend[0].clear();   // (a job that failed half-way leaves nothing behind for the next one)
     d.pend[1].clear();
+    if (j.mode == 64) CUS(d.partial.ensure(((hi - lo + chunk - 1) / chunk + 1) * 576));
     auto pageable = [](const void *p) {
         cudaPointerAttributes a;
         if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -703,6 +748,40 @@ static int32_t run_slice(zkp_ctx *ctx, DevState &d, const HostJob &j, size_t lo,
             CUS(d2h(B_G2, j.og2 + c0 * 24, B[B_G2].p, cn * 192));
             CUS(d2h(B_G1INF, j.og1inf + c0, B[B_G1INF].p, cn));
             CUS(d2h(B_G2INF, j.og2inf + c0, B[B_G2INF].p, cn));
+        } else if (j.mode == 64) {
+            // One product over all pairs of the slice: the pairs of a chunk are grouped four to a lane pair and
+            // run as shared-accumulator Miller loops (one Fp12 squaring chain per FOUR pairs: 4,684 instead of
+            // 6,916 Fp products per pair), the chunk's outputs are folded to one Fp12 in
+            // d.partial[chunk].  Same two-stream pipeline as the independent pairings: the copies of one chunk
+            // overlap the kernels of the other; nothing returns to the host per chunk.
+            size_t ci = (c0 - lo) / chunk, nc4 = cn / ZKP_PRODUCT_GROUP, rem = cn % ZKP_PRODUCT_GROUP, ne = nc4 + (rem ? 1 : 0);
+            const uint8_t *di1 = nullptr, *di2 = nullptr;
+            CUS(B[B_G1].ensure(cn * 96));
+            CUS(B[B_G2].ensure(cn * 192));
+            CUS(B[B_OUT].ensure(ne * 576));
+            CUS(B[B_IN].ensure(zkp_product_scratch_elems(ne) * 576));   // this buffer set's product scratch
+            CUS(h2d(B_G1, B[B_G1].p, j.g1 + c0 * 12, cn * 96));
+            CUS(h2d(B_G2, B[B_G2].p, j.g2 + c0 * 24, cn * 192));
+            if (j.g1inf) {
+                CUS(B[B_G1INF].ensure(cn));
+                CUS(h2d(B_G1INF, B[B_G1INF].p, j.g1inf + c0, cn));
+                di1 = (const uint8_t *)B[B_G1INF].p;
+            }
+            if (j.g2inf) {
+                CUS(B[B_G2INF].ensure(cn));
+                CUS(h2d(B_G2INF, B[B_G2INF].p, j.g2inf + c0, cn));
+                di2 = (const uint8_t *)B[B_G2INF].p;
+            }
+            if (nc4)
+                CUS(launch_pairing(ctx, d, 1, (const uint64_t *)B[B_G1].p, di1, (const uint64_t *)B[B_G2].p, di2, nc4, ZKP_PRODUCT_GROUP,
+                                   nullptr, (uint64_t *)B[B_OUT].p, nullptr, d.d_err, st));
+            if (rem) {
+                size_t o = nc4 * ZKP_PRODUCT_GROUP;
+                CUS(launch_pairing(ctx, d, 1, (const uint64_t *)B[B_G1].p + 12 * o, di1 ? di1 + o : nullptr,
+                                   (const uint64_t *)B[B_G2].p + 24 * o, di2 ? di2 + o : nullptr, 1, (int)rem, nullptr,
+                                   (uint64_t *)B[B_OUT].p + 72 * nc4, nullptr, d.d_err, st));
+            }
+            CUS(launch_product(ctx, (const uint64_t *)B[B_OUT].p, ne, (uint64_t *)B[B_IN].p, (uint64_t *)d.partial.p + 72 * ci, d.d_err, st));
         } else {
             size_t np = cn * (size_t)j.k, p0 = c0 * (size_t)j.k;
             size_t nq = cn * (size_t)(j.k - j.kf), q0 = c0 * (size_t)(j.k - j.kf);   // per-check G2 points
@@ -748,6 +827,13 @@ static int32_t run_slice(zkp_ctx *ctx, DevState &d, const HostJob &j, size_t lo,
     flush(0);
     CUS(cudaStreamSynchronize(d.stream[1]));
     flush(1);
+    if (j.mode == 64) {   // fold this device's chunk partials into the slot after the last one
+        size_t nchunks = (hi - lo + chunk - 1) / chunk;
+        CUS(d.buf[0][B_IN].ensure(zkp_product_scratch_elems(nchunks) * 576));
+        CUS(launch_product(ctx, (const uint64_t *)d.partial.p, nchunks, (uint64_t *)d.buf[0][B_IN].p,
+                           (uint64_t *)d.partial.p + 72 * nchunks, d.d_err, d.stream[0]));
+        CUS(cudaStreamSynchronize(d.stream[0]));
+    }
     uint32_t herr = 0;
     CUS(cudaMemcpy(&herr, d.d_err, sizeof herr, cudaMemcpyDeviceToHost));
     if (herr & 1) {
@@ -845,6 +931,7 @@ int32_t zkp_g2_prepare_batch(zkp_ctx *ctx, const uint64_t *g2_xy, size_t n, uint
     if (!g2_xy || !out_tables) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState &d = ctx->devs[0];   // a handful of verifying-key points: one device
+    DeviceGuard guard;
     CU(cudaSetDevice(d.id));
     cudaStream_t st = d.stream[0];
     DevBuf *B = d.buf[0];
@@ -869,8 +956,9 @@ int32_t zkp_g2_prepare_dev(zkp_ctx *ctx, int32_t dev, const uint64_t *d_g2_xy, s
     if (n && (!d_g2_xy || !d_out_tables)) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState &d = ctx->devs[dev];
+    DeviceGuard guard;
     CU(cudaSetDevice(d.id));
-    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream (CUDA convention)
     if (n) {
         k_g2_prepare<<<grid_for(n), ZKP_TPB, 0, st>>>(d_g2_xy, (Fp *)d_out_tables, d_err, n);
         ctx->launches++;
@@ -899,8 +987,9 @@ int32_t zkp_multi_pairing_prepared_dev(zkp_ctx *ctx, int32_t dev, const uint64_t
     if (!d_g1 || !d_out || (kf < k && !d_g2) || (kf && !d_tables)) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState &d = ctx->devs[dev];
+    DeviceGuard guard;
     CU(cudaSetDevice(d.id));
-    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream (CUDA convention)
     CU(launch_pairing(ctx, d, 3, d_g1, d_g1inf, d_g2, d_g2inf, n_checks, k, nullptr, d_out, d_is_one, d_err, st, d_tables, d_tables_inf, kf));
     return ZKP_OK;
 }
@@ -913,8 +1002,9 @@ int32_t zkp_fp_bytes_dev(zkp_ctx *ctx, int32_t dev, int32_t dir, const void *d_i
     if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return fail(ZKP_ERR_INVALID_ARG, "buffers must be 16-byte aligned");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState &d = ctx->devs[dev];
+    DeviceGuard guard;
     CU(cudaSetDevice(d.id));
-    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream (CUDA convention)
     if (n) {
         k_fp_bytes<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dir, (const uint4 *)d_in, (uint4 *)d_out, d_ok, n);
         ctx->launches++;
@@ -928,6 +1018,7 @@ static int32_t bytes_job(zkp_ctx *ctx, int dir, const void *in, void *out, uint8
     if (!in || !out) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState &d = ctx->devs[0];   // HBM-bound byte shuffling: one device is already PCIe-limited
+    DeviceGuard guard;
     CU(cudaSetDevice(d.id));
     cudaStream_t st = d.stream[0];
     DevBuf *B = d.buf[0];
@@ -985,79 +1076,29 @@ int32_t zkp_g2_mul_batch(zkp_ctx *ctx, const uint64_t *g2_xy, const uint8_t *g2_
     return group_job(ctx, GOP_G2_MUL, g2_xy, g2_inf, scalars, n, out_xy, out_inf);
 }
 
-// One large product: per-device Miller loops over a contiguous slice -> per-device Fp12 partial ->
-// gather the 576-byte partials on the first device -> multiply -> ONE final exponentiation.
+// One large product: per-device shared-accumulator Miller loops over a contiguous slice -> per-device Fp12
+// partial -> gather the 576-byte partials on the first device -> multiply -> ONE final exponentiation.
 int32_t zkp_multi_miller_product(zkp_ctx *ctx, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
                                  size_t n, uint64_t *out_miller_product, uint64_t *out_gt) {
     if (!ctx) return fail(ZKP_ERR_INVALID_ARG, "ctx is NULL");
     if (!g1 || !g2 || n == 0) return fail(ZKP_ERR_INVALID_ARG, "NULL buffer or n == 0");
     std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard guard;
     size_t nd = ctx->devs.size();
-    if (n < nd) nd = 1;
+    if (n < 2 * nd) nd = 1;
+    HostJob j;
+    j.mode = 64; j.g1 = g1; j.g1inf = g1inf; j.g2 = g2; j.g2inf = g2inf;
     std::vector<int32_t> rcs(nd, ZKP_OK);
     std::vector<std::string> msgs(nd);
-    // each device: chunks of Miller loops, each chunk folded to one Fp12 appended to d.partial
-    auto worker = [&](size_t di) {
-        DevState &d = ctx->devs[di];
-        std::string &msg = msgs[di];
-        int32_t &rc = rcs[di];
-#define CUW(call)                                                                     \
-    do {                                                                              \
-        cudaError_t e_ = (call);                                                      \
-        if (e_ != cudaSuccess) {                                                      \
-            msg = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
-            rc = ZKP_ERR_CUDA;                                                        \
-            return;                                                                   \
-        }                                                                             \
-    } while (0)
-        size_t lo, hi;
-        slice_of(n, nd, di, lo, hi);
-        CUW(cudaSetDevice(d.id));
-        cudaStream_t st = d.stream[0];
-        CUW(cudaMemsetAsync(d.d_err, 0, sizeof(uint32_t), st));
-        size_t chunk = ZKP_CHUNK, nchunks = (hi - lo + chunk - 1) / chunk;
-        CUW(d.partial.ensure((nchunks + 1) * 576));
-        CUW(d.scratch.ensure(zkp_product_scratch_elems(chunk) * 576));
-        DevBuf *B = d.buf[0];
-        size_t ci = 0;
-        for (size_t c0 = lo; c0 < hi; c0 += chunk, ci++) {
-            size_t cn = hi - c0 < chunk ? hi - c0 : chunk;
-            CUW(B[B_G1].ensure(cn * 96));
-            CUW(B[B_G2].ensure(cn * 192));
-            CUW(B[B_OUT].ensure(cn * 576));
-            CUW(cudaMemcpyAsync(B[B_G1].p, g1 + c0 * 12, cn * 96, cudaMemcpyHostToDevice, st));
-            CUW(cudaMemcpyAsync(B[B_G2].p, g2 + c0 * 24, cn * 192, cudaMemcpyHostToDevice, st));
-            const uint8_t *di1 = nullptr, *di2 = nullptr;
-            if (g1inf) {
-                CUW(B[B_G1INF].ensure(cn));
-                CUW(cudaMemcpyAsync(B[B_G1INF].p, g1inf + c0, cn, cudaMemcpyHostToDevice, st));
-                di1 = (const uint8_t *)B[B_G1INF].p;
-            }
-            if (g2inf) {
-                CUW(B[B_G2INF].ensure(cn));
-                CUW(cudaMemcpyAsync(B[B_G2INF].p, g2inf + c0, cn, cudaMemcpyHostToDevice, st));
-                di2 = (const uint8_t *)B[B_G2INF].p;
-            }
-            CUW(launch_pairing(ctx, d, 1, (const uint64_t *)B[B_G1].p, di1, (const uint64_t *)B[B_G2].p, di2, cn, 1, nullptr,
-                               (uint64_t *)B[B_OUT].p, nullptr, d.d_err, st));
-            CUW(launch_product(ctx, (const uint64_t *)B[B_OUT].p, cn, (uint64_t *)d.scratch.p, (uint64_t *)d.partial.p + 72 * ci, d.d_err, st));
-        }
-        // fold this device's chunk partials into slot `nchunks`
-        CUW(launch_product(ctx, (const uint64_t *)d.partial.p, nchunks, (uint64_t *)d.scratch.p, (uint64_t *)d.partial.p + 72 * nchunks, d.d_err, st));
-        CUW(cudaStreamSynchronize(st));
-        uint32_t herr = 0;
-        CUW(cudaMemcpy(&herr, d.d_err, sizeof herr, cudaMemcpyDeviceToHost));
-        if (herr & 1) {
-            msg = "input limb vector >= p (non-canonical field element)";
-            rc = ZKP_ERR_NONCANONICAL;
-        }
-#undef CUW
-    };
     if (nd == 1) {
-        worker(0);
+        rcs[0] = run_slice(ctx, ctx->devs[0], j, 0, n, msgs[0]);
     } else {
         std::vector<std::thread> th;
-        for (size_t di = 0; di < nd; di++) th.emplace_back(worker, di);
+        for (size_t di = 0; di < nd; di++) {
+            size_t lo, hi;
+            slice_of(n, nd, di, lo, hi);
+            th.emplace_back([&, di, lo, hi]() { rcs[di] = run_slice(ctx, ctx->devs[di], j, lo, hi, msgs[di]); });
+        }
         for (auto &t : th) t.join();
     }
     for (size_t di = 0; di < nd; di++)
@@ -1096,6 +1137,7 @@ int32_t zkp_imad_peak(zkp_ctx *ctx, int32_t dev, int32_t kind, double *macs_per_
     if (!macs_per_second || kind < 0 || kind > 2) return fail(ZKP_ERR_INVALID_ARG, "bad kind / NULL out");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DevState &d = ctx->devs[dev];
+    DeviceGuard guard;
     CU(cudaSetDevice(d.id));
     cudaStream_t st = d.stream[0];
     uint32_t *sink = d.d_err;

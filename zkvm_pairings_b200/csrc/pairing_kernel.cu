@@ -20,7 +20,8 @@
 #include "fe_scratch.cuh"
 
 // fe_kernel.cu
-cudaError_t zkp_launch_fe_stages(void *scratch, size_t n, uint64_t *out, uint8_t *is_one, cudaStream_t st, int *launches);
+cudaError_t zkp_launch_fe_stages(void *scratch, size_t n, uint64_t *out, uint8_t *is_one, cudaStream_t st, const ZkpFeAux *aux,
+                                 int *launches);
 
 #ifndef ZKP_TPB
 #define ZKP_TPB 128           // threads per block
@@ -73,7 +74,7 @@ static int pair_capacity(int k) { return k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : 
 // `scratch`: zkp_fe_scratch_bytes(n) device bytes when mode has bit1 set (else unused)
 cudaError_t zkp_launch_k_pairing(int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2, const uint8_t *g2inf,
                                  size_t n, int k, const uint64_t *in12, uint64_t *out, uint8_t *is_one, uint32_t *err,
-                                 void *scratch, const void *tab, const uint8_t *tabinf, int kf, cudaStream_t st, int *launches) {
+                                 void *scratch, const void *tab, const uint8_t *tabinf, int kf, cudaStream_t st, const ZkpFeAux *aux, int *launches) {
     if (n == 0) return cudaSuccess;
     FeScratch fs;
     fs.lanes = (Fp *)scratch;
@@ -89,7 +90,7 @@ cudaError_t zkp_launch_k_pairing(int mode, const uint64_t *g1, const uint8_t *g1
     *launches = 1;
     if (mode & ZKP_DO_FINAL_EXP) {
         int nl = 0;
-        cudaError_t rc = zkp_launch_fe_stages(scratch, n, out, is_one, st, &nl);
+        cudaError_t rc = zkp_launch_fe_stages(scratch, n, out, is_one, st, aux, &nl);
         *launches += nl;
         if (rc != cudaSuccess) return rc;
     }

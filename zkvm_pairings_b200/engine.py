@@ -346,7 +346,8 @@ class PairingEngine:
     def pairing_dev(self, mode: int, out, g1=None, g2=None, g1_inf=None, g2_inf=None, in_fp12=None, n_checks=None,
                     pairs_per_check: int = 1, is_one=None, err=None, stream: int = 0, dev: int = 0):
         """Asynchronous launch on device-resident buffers (torch CUDA tensors).  ``stream`` is a raw
-        cudaStream_t handle (e.g. ``torch.cuda.current_stream().cuda_stream``); 0 = the context's."""
+        cudaStream_t handle (``torch.cuda.current_stream().cuda_stream``); 0 = the legacy default stream,
+        which is also torch's default stream, so the launch is ordered with the caller's torch work."""
         if n_checks is None:
             n_checks = out.numel() // 72
         self._check(self._lib.zkp_pairing_dev(self._ctx, dev, mode, _dptr(g1), _dptr(g1_inf), _dptr(g2), _dptr(g2_inf), n_checks,
