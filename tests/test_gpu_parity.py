@@ -401,6 +401,166 @@ def test_group_addition_matches_oracle(engine, coracle):
         assert not flag.any() and np.array_equal(d2, dbl)
 
 
+def test_config3_full_size_2p18_checks(engine, coracle):
+    """BASELINE config[3] at its stated size: 2^18 Groth16-shaped 4-pair checks with a shared final
+    exponentiation, a seeded 1 % of them corrupted.  Every is_one flag against the construction, the prepared
+    (G2Prepared line tables for the three verifying-key points) path bit-identical to the plain one over the
+    whole batch, and a strided sample of Gt values against the C oracle."""
+    from zkvm_pairings_b200 import workloads
+    n = 1 << int(os.environ.get("ZKP_TEST_CONFIG3_LOG2", "18"))
+    wl = workloads.groth16_checks(engine, n)
+    gt, one = engine.multi_pairing_batch(wl["g1"], wl["g2"], 4)
+    assert np.array_equal(one.astype(bool), wl["expect_one"])
+    assert wl["expect_one"].sum() == n - len(range(7, n, 100))
+    tab = engine.g2_prepare_batch(wl["fixed"])
+    gtp, onep = engine.multi_pairing_prepared_batch(wl["g1"], wl["g2_var"], 4, tab)
+    assert np.array_equal(gtp, gt) and np.array_equal(onep, one)
+    idx = np.unique(np.concatenate([np.arange(0, n, max(1, n // 48)), np.arange(7, n, max(100, 100 * (n // 1600)))]))
+    g1s = np.ascontiguousarray(wl["g1"].reshape(n, 4, 12)[idx]).reshape(-1, 12)
+    g2s = np.ascontiguousarray(wl["g2"].reshape(n, 4, 24)[idx]).reshape(-1, 24)
+    exp, eone = coracle.multi_pairing_batch(g1s, None, g2s, None, 4)
+    assert np.array_equal(gt[idx], exp) and np.array_equal(one[idx], eone)
+    assert not eone.all() and eone.any()          # the sample holds valid and corrupted checks
+
+
+def test_config2_full_size_2p20_final_exp_only(engine, coracle):
+    """BASELINE config[2] at its stated size: the final exponentiation alone over 2^20 Miller-loop outputs:
+    every element equal to the one-call pairing of the same points, a strided sample against the C oracle."""
+    n = 1 << int(os.environ.get("ZKP_TEST_CONFIG2_LOG2", "20"))
+    g1, _, g2, _ = engine.gen_points(0xFE20, 0, n)
+    ml = engine.miller_loop_batch(g1, g2)
+    fe = engine.final_exponentiation_batch(ml)
+    assert np.array_equal(fe, engine.pairing_batch(g1, g2))
+    idx = np.arange(0, n, n // 64)
+    assert np.array_equal(fe[idx], coracle.final_exp_batch(np.ascontiguousarray(ml[idx])))
+    assert np.array_equal(ml[idx], coracle.miller_loop_batch(np.ascontiguousarray(g1[idx]), None, np.ascontiguousarray(g2[idx]), None))
+
+
+def test_multi_miller_product_grouping_and_chunks(engine, coracle):
+    """zkp_multi_miller_product streams 2^18-pair chunks through two buffer sets and runs FOUR pairs per
+    shared-accumulator Miller loop: sizes that leave a ragged group (n % 4 != 0), cross a chunk boundary, and
+    carry points at infinity must give the same field element as the product of the per-pair outputs."""
+    import torch
+    for n, seed in ((1, 5), (3, 6), (6, 7), (1029, 8), ((1 << 18) + 5, 9)):
+        g1, i1, g2, i2 = engine.gen_points(seed, 0, n)
+        if n > 4:
+            i1[2] = 1
+            i2[n - 1] = 1
+        prod, gt = engine.multi_miller_product(g1, g2, i1, i2)
+        if n <= 2048:
+            eml, egt = coracle.miller_product(g1, i1, g2, i2)
+            assert np.array_equal(prod, eml) and np.array_equal(gt, egt), n
+        ml = engine.miller_loop_batch(g1, g2, i1, i2)
+        d_in = torch.from_numpy(ml.view(np.int64)).cuda()
+        scratch = torch.empty(engine.product_scratch_elems(n) * 72, dtype=torch.int64, device="cuda")
+        d_out = torch.empty(72, dtype=torch.int64, device="cuda")
+        engine.fp12_product_dev(d_in, n, scratch, d_out, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy().view(np.uint64), prod), n
+        assert np.array_equal(engine.final_exponentiation_batch(prod[None])[0], gt), n
+
+
+def test_default_stream_ordering_and_device_restored(engine, coracle):
+    """*_dev calls with stream = 0 run on the legacy default stream, i.e. ordered after torch's default-stream
+    work that produced their inputs and before the torch work that consumes their outputs -- no explicit
+    synchronisation in between; the caller's current device is untouched."""
+    import torch
+    assert torch.cuda.current_stream().cuda_stream == 0
+    n = 4096
+    g1, _, g2, _ = util.oracle_points(coracle, 31337, 0, 64)
+    reps = n // 64
+    before = torch.cuda.current_device()
+    big = torch.zeros((1 << 26,), dtype=torch.int64, device="cuda")          # keeps the default stream busy first
+    big += 1
+    dg1 = torch.from_numpy(np.tile(g1, (reps, 1)).view(np.int64)).cuda(non_blocking=True)
+    dg2 = torch.from_numpy(np.tile(g2, (reps, 1)).view(np.int64)).cuda(non_blocking=True)
+    out = torch.zeros((n, 72), dtype=torch.int64, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    engine.pairing_dev(3, out, g1=dg1, g2=dg2, err=err, stream=0)
+    host = out.cpu()                                                          # default-stream consumer, no sync call
+    assert torch.cuda.current_device() == before
+    exp = coracle.pairing_batch(g1, None, g2, None)
+    assert np.array_equal(host.numpy().view(np.uint64)[:64], exp) and np.array_equal(host.numpy().view(np.uint64)[-64:], exp)
+    assert int(err.item()) == 0
+
+
+def _all_devices_engine():
+    import zkvm_pairings_b200 as z
+    if z.device_count() < 2:
+        pytest.skip("needs >= 2 CUDA devices (run with gpurun --gpus 2)")
+    return z.PairingEngine()
+
+
+def test_multi_device_context_matches_single_device(engine, coracle):
+    """The in-library multi-device paths (one host thread + two streams per device, contiguous slices; the
+    576-byte Fp12 partial gather of zkp_multi_miller_product over peer copies): bit-identical to the
+    single-device engine and the oracle, for sizes that do not divide evenly and for n < 2 * devices."""
+    import torch
+    multi = _all_devices_engine()
+    try:
+        nd = multi.num_devices
+        assert nd >= 2
+        before = torch.cuda.current_device()
+        for n in (1, nd + 1, 2 * nd - 1, 5003, (1 << 18) + 77):
+            g1, i1, g2, i2 = engine.gen_points(0xD0 + n, 0, n)
+            if n > 8:
+                i1[3] = 1
+            gt = multi.pairing_batch(g1, g2, i1, i2)
+            assert np.array_equal(gt, engine.pairing_batch(g1, g2, i1, i2)), n
+            if n <= 5003:
+                assert np.array_equal(gt, coracle.pairing_batch(g1, i1, g2, i2)), n
+            prod, pgt = multi.multi_miller_product(g1, g2, i1, i2)
+            sprod, sgt = engine.multi_miller_product(g1, g2, i1, i2)
+            assert np.array_equal(prod, sprod) and np.array_equal(pgt, sgt), n
+            if n <= 5003:
+                eml, egt = coracle.miller_product(g1, i1, g2, i2)
+                assert np.array_equal(prod, eml) and np.array_equal(pgt, egt), n
+        n = 4 * 1001
+        g1, i1, g2, i2 = engine.gen_points(0xD4, 0, n)
+        out, one = multi.multi_pairing_batch(g1, g2, 4, i1, i2)
+        sout, sone = engine.multi_pairing_batch(g1, g2, 4, i1, i2)
+        assert np.array_equal(out, sout) and np.array_equal(one, sone)
+        exp, eone = coracle.multi_pairing_batch(g1[:400], None, g2[:400], None, 4)
+        assert np.array_equal(out[:100], exp)
+        assert torch.cuda.current_device() == before      # the context never leaves the caller on another device
+    finally:
+        multi.close()
+
+
+def test_config5_sharded_2p24_with_product_gather(engine, coracle):
+    """BASELINE config[4] ("2^24 independent pairings sharded across 2/4/8 B200 with Fp12 partial-product
+    gather"): one multi-device context, pageable host buffers.  Independent Gt outputs: a sample of every
+    device's slice against the C oracle; the global product through the gather equals the final exponentiation
+    of the product of all per-pair Miller outputs folded on ONE device."""
+    import torch
+    multi = _all_devices_engine()
+    try:
+        nd = multi.num_devices
+        n = 1 << int(os.environ.get("ZKP_TEST_CONFIG5_LOG2", "24"))
+        g1, _, g2, _ = multi.gen_points(0xC5, 0, n)
+        gt = multi.pairing_batch(g1, g2)
+        idx = np.concatenate([np.arange(d * n // nd, d * n // nd + 8) for d in range(nd)] + [np.arange(n - 8, n)])
+        assert np.array_equal(gt[idx], coracle.pairing_batch(np.ascontiguousarray(g1[idx]), None, np.ascontiguousarray(g2[idx]), None))
+        prod, pgt = multi.multi_miller_product(g1, g2)
+        # single-device fold of the per-pair Miller outputs, chunk by chunk (2^22 pairs = 2.4 GB at a time)
+        parts = []
+        step = 1 << 22
+        for lo in range(0, n, step):
+            ml = engine.miller_loop_batch(g1[lo:lo + step], g2[lo:lo + step])
+            d_in = torch.from_numpy(ml.view(np.int64)).cuda()
+            scratch = torch.empty(engine.product_scratch_elems(len(ml)) * 72, dtype=torch.int64, device="cuda")
+            d_out = torch.empty(72, dtype=torch.int64, device="cuda")
+            engine.fp12_product_dev(d_in, len(ml), scratch, d_out, stream=0)
+            parts.append(d_out.cpu().numpy().view(np.uint64))
+        acc = parts[0]
+        for p in parts[1:]:
+            acc = engine.fp12_mul_batch(acc[None], p[None])[0]
+        assert np.array_equal(acc, prod)
+        assert np.array_equal(engine.final_exponentiation_batch(prod[None])[0], pgt)
+    finally:
+        multi.close()
+
+
 def test_imad_peak_probe(engine):
     wide = engine.imad_peak(0)
     lo = engine.imad_peak(1)

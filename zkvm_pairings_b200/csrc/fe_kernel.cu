@@ -15,6 +15,12 @@
 #define ZKP_FE_SYNC 4
 #endif
 #define ZKP_LOOP_SYNC ZKP_FE_SYNC
+#ifndef ZKP_FE_SMEM
+#define ZKP_FE_SMEM 0          // 1: the running state of the compressed squaring chains lives in shared memory (pairing.cuh cexp_begin)
+#endif
+#if ZKP_FE_SMEM
+#define ZKP_CEXP_Z_SMEM 1
+#endif
 #include "../../include/zkpair.h"
 #include "fe_scratch.cuh"
 
@@ -31,6 +37,8 @@
 #endif
 
 using namespace zkp;
+
+#define ZKP_FE_SMEM_BYTES (ZKP_FE_SMEM ? (size_t)208 * ZKP_TPB : (size_t)0)
 
 extern "C" void zkp_fe_geometry(int *tpb, int *blocks, int *sync) { *tpb = ZKP_TPB; *blocks = ZKP_MIN_BLOCKS_FE; *sync = ZKP_FE_SYNC; }
 extern "C" size_t zkp_fe_scratch_bytes(size_t n) { return n * (2 * ZKP_FE_LANE_FP + 1) * sizeof(Fp); }
@@ -114,10 +122,10 @@ cudaError_t zkp_launch_fe_stages(void *scratch, size_t n, uint64_t *out, uint8_t
     size_t ta = (na + ZKP_INV_RUN - 1) / ZKP_INV_RUN, tb = (nb + ZKP_INV_RUN - 1) / ZKP_INV_RUN;
     for (int stage = 0; stage < ZKP_FE_STAGES; stage++) {
         k_fe_batch_inv<<<(unsigned)((ta + 127) / 128), 128, 0, st>>>(fs.norm, na);
-        k_fe_stage<<<ga, b, 0, st>>>(stage, fs, out, is_one, 0, na);
+        k_fe_stage<<<ga, b, ZKP_FE_SMEM_BYTES, st>>>(stage, fs, out, is_one, 0, na);
         if (nb) {
             k_fe_batch_inv<<<(unsigned)((tb + 127) / 128), 128, 0, s2>>>(fs.norm + na, nb);
-            k_fe_stage<<<gb, b, 0, s2>>>(stage, fs, out, is_one, na, n);
+            k_fe_stage<<<gb, b, ZKP_FE_SMEM_BYTES, s2>>>(stage, fs, out, is_one, na, n);
         }
     }
     *launches = 2 * ZKP_FE_STAGES * (nb ? 2 : 1);

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) k_fp_bytes(int dir, const uint4 *__restri
 // independent 32-bit IMAD chains; KIND 2: the carry-chained wide MACs exactly as the Montgomery
 // rows of fp.cuh issue them (row_mad: two 6-MAC carry chains per step).
 template <int KIND>
-__global__ void __launch_bounds__(256) k_imad_peak(uint32_t *sink, int iters) {
+__global__ void __launch_bounds__(512) k_imad_peak(uint32_t *sink, int iters) {
     uint32_t x = threadIdx.x * 2654435761u + 12345u, y = blockIdx.x * 40503u + 977u;
     uint32_t m = x;
     if (KIND == 0) {
@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t *sink, int iters) {
 #pragma unroll
         for (int c = 0; c < 8; c++) { acc[c] = x + c; ys[c] = y * (2 * c + 3) + sink[1]; }
         for (int it = 0; it < iters; it++) {
-            m = m * 1664525u + 1013904223u;
+            asm volatile("shf.l.wrap.b32 %0, %0, %0, 7;" : "+r"(m));   // rotate + add (SHF, IADD3): only the counted MACs touch the multiply pipe
+            m += 0x9E3779B9u;
 #pragma unroll
             for (int c = 0; c < 8; c++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(m), "r"(ys[c]));
         }
@@ -187,7 +188,8 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t *sink, int iters) {
 #pragma unroll
         for (int c = 0; c < 8; c++) { acc[c] = x + c; ys[c] = y * (2 * c + 3) + sink[1]; }
         for (int it = 0; it < iters; it++) {
-            m = m * 1664525u + 1013904223u;
+            asm volatile("shf.l.wrap.b32 %0, %0, %0, 7;" : "+r"(m));   // rotate + add (SHF, IADD3): only the counted MACs touch the multiply pipe
+            m += 0x9E3779B9u;
 #pragma unroll
             for (int c = 0; c < 8; c++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[c]) : "r"(m), "r"(ys[c]));
         }
@@ -200,7 +202,8 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t *sink, int iters) {
 #pragma unroll
         for (int c = 0; c < 12; c++) { ev[c] = x + c; od[c] = y + c; a[c] = x * (c + 3) + y + sink[1]; }
         for (int it = 0; it < iters; it++) {
-            m = m * 1664525u + 1013904223u;
+            asm volatile("shf.l.wrap.b32 %0, %0, %0, 7;" : "+r"(m));   // rotate + add (SHF, IADD3): only the counted MACs touch the multiply pipe
+            m += 0x9E3779B9u;
             row_mad(ev, od, a, m);
         }
         uint32_t s = 0;
@@ -1141,29 +1144,36 @@ int32_t zkp_imad_peak(zkp_ctx *ctx, int32_t dev, int32_t kind, double *macs_per_
     CU(cudaSetDevice(d.id));
     cudaStream_t st = d.stream[0];
     uint32_t *sink = d.d_err;
-    const int iters = 1 << 13, blocks = d.sms * 8, threads = 256;
+    // every issued multiply is counted (the multiplicand update is a shift + add on the ALU pipe); the launch
+    // geometry is swept and the best sustained rate is the roofline denominator
+    const int iters = 1 << 13;
     const double per_thread = (double)iters * (kind == 2 ? 12.0 : 8.0);
+    static const int geom[][2] = {{8, 256}, {4, 256}, {16, 128}, {8, 128}, {4, 512}};   // blocks per SM, threads per block
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
-    float best = 1e30f;
-    for (int rep = 0; rep < 4; rep++) {
-        CU(cudaEventRecord(e0, st));
-        if (kind == 0) k_imad_peak<0><<<blocks, threads, 0, st>>>(sink + 0, iters);
-        else if (kind == 1) k_imad_peak<1><<<blocks, threads, 0, st>>>(sink + 0, iters);
-        else k_imad_peak<2><<<blocks, threads, 0, st>>>(sink + 0, iters);
-        ctx->launches++;
-        CU(cudaEventRecord(e1, st));
-        CU(cudaEventSynchronize(e1));
-        float ms = 0;
-        CU(cudaEventElapsedTime(&ms, e0, e1));
-        if (rep > 0 && ms < best) best = ms;
+    double best_rate = 0;
+    for (const auto &g : geom) {
+        const int blocks = d.sms * g[0], threads = g[1];
+        for (int rep = 0; rep < 3; rep++) {
+            CU(cudaEventRecord(e0, st));
+            if (kind == 0) k_imad_peak<0><<<blocks, threads, 0, st>>>(sink + 0, iters);
+            else if (kind == 1) k_imad_peak<1><<<blocks, threads, 0, st>>>(sink + 0, iters);
+            else k_imad_peak<2><<<blocks, threads, 0, st>>>(sink + 0, iters);
+            ctx->launches++;
+            CU(cudaEventRecord(e1, st));
+            CU(cudaEventSynchronize(e1));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            double rate = per_thread * blocks * threads / (ms * 1e-3);
+            if (rep > 0 && rate > best_rate) best_rate = rate;
+        }
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     CU(cudaMemsetAsync(d.d_err, 0, sizeof(uint32_t), st));
     CU(cudaStreamSynchronize(st));
-    *macs_per_second = per_thread * blocks * threads / (best * 1e-3);
+    *macs_per_second = best_rate;
     return ZKP_OK;
 }
 

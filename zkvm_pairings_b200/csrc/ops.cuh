@@ -196,13 +196,14 @@ enum { ZKP_DO_MILLER = 1, ZKP_DO_FINAL_EXP = 2 };
 template <int K>
 ZKP_HD void pairing_front(Fp12 &f, bool &bad, int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2,
                           const uint8_t *g2inf, int k, const uint64_t *in12, const Fp *tab = nullptr,
-                          const uint8_t *tabinf = nullptr, int kf = 0) {
+                          const uint8_t *tabinf = nullptr, int kf = 0, G2P *rs_ext = nullptr) {
     // k pairs in total; the last kf of them take their G2 lines from the prepared tables `tab`
     // (then g2 / g2inf hold only the k - kf per-check points)
     if (mode & ZKP_DO_MILLER) {
         G1A ps[K];
         G2A qs[K];
-        G2P rs[K];
+        G2P rs_local[K];
+        G2P *rs = rs_ext ? rs_ext : rs_local;   // the caller may keep the G2 accumulators elsewhere (shared memory)
         bool skip[K];
         const int kv = k - kf;
         for (int j = 0; j < k; j++) {

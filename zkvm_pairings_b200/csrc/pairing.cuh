@@ -223,7 +223,15 @@ ZKP_HD Fp2 cexp_den(const Fp2 *z) {
 }
 // first half: the compressed run and the product of the denominators; returns the norm to invert
 ZKP_NOINLINE Fp cexp_begin(CExp &c, const Fp12 &f) {
+#if defined(ZKP_DEVICE_BUILD) && defined(ZKP_CEXP_Z_SMEM)
+    // the four running coefficients of the compressed chain in SHARED memory (fe_kernel.cu): per-thread slice of
+    // 208 bytes = 52 words (20 mod 32: the 128-bit accesses of a quarter-warp hit disjoint bank groups)
+    extern __shared__ uint4 zkp_cexp_smem[];
+    Fp2 *z = reinterpret_cast<Fp2 *>(reinterpret_cast<char *>(zkp_cexp_smem) + (size_t)threadIdx.x * 208);
+    z[0] = f.c1.c0; z[1] = f.c0.c2; z[2] = f.c0.c1; z[3] = f.c1.c2;
+#else
     Fp2 z[4] = {f.c1.c0, f.c0.c2, f.c0.c1, f.c1.c2};
+#endif
     int k = 0;
 #pragma unroll 1
     for (int i = 1; i <= ZKP_CEXP_RUN; i++) {

@@ -32,6 +32,16 @@ cudaError_t zkp_launch_fe_stages(void *scratch, size_t n, uint64_t *out, uint8_t
 
 using namespace zkp;
 
+// ZKP_SMEM_STATE: 0 = all per-thread state in thread-local memory, 1 = f in shared memory, 2 = f and (K = 1) R.
+// Measured (profiles/r2b_smem_state_variants.txt): Miller loop at 2^20 280.5 ms (0) -> 276.6 (1) / 276.9 (2); DRAM traffic
+// of the kernel 15.8 -> 6.3 GB per 2^16 pairings, local loads -25 %, local stores -16 %; with 3 blocks per SM (168
+// registers) 286.2 ms.  The spill traffic was not what bounds the kernel: the multiply pipe stays at 80 %.
+#ifndef ZKP_SMEM_STATE
+#define ZKP_SMEM_STATE 2
+#endif
+// bytes of shared memory per thread: 304 = 76 words (f + 16 pad), 432 = 108 words (f + R); both are 12 mod 32 words
+#define ZKP_SMEM_STRIDE(K) (((K) == 1 && ZKP_SMEM_STATE >= 2) ? 432 : 304)
+
 // mode: bit0 Miller loop, bit1 first half of the final exponentiation.  One lane pair per check of
 // k (<= K) pairs.  Without bit1 the Miller output is stored canonically to `out`.
 template <int K>
@@ -45,9 +55,20 @@ k_pairing(int mode, const uint64_t *__restrict__ g1, const uint8_t *__restrict__
     if (!live) i = n - 1;   // stay converged: redo the last element, store nothing
     size_t e = i * (size_t)k, e2 = i * (size_t)(k - kf);   // the last kf pairs of a check use prepared G2 tables
     bool bad = false;
+#if ZKP_SMEM_STATE
+    // The Miller accumulator f (and, for single pairings, the G2 accumulator R) live in SHARED memory: a per-thread
+    // slice at a stride whose word count is 12 mod 32, so that the 128-bit accesses of a quarter-warp fall into
+    // disjoint bank groups (conflict-free) -- fixed ~30-cycle latency instead of thread-local frames that miss L1.
+    extern __shared__ uint4 zkp_smem[];
+    char *slice = reinterpret_cast<char *>(zkp_smem) + (size_t)threadIdx.x * ZKP_SMEM_STRIDE(K);
+    Fp12 &f = *reinterpret_cast<Fp12 *>(slice);
+    G2P *rs_ext = (K == 1 && ZKP_SMEM_STATE >= 2) ? reinterpret_cast<G2P *>(slice + sizeof(Fp12)) : nullptr;
+#else
     Fp12 f;
+    G2P *rs_ext = nullptr;
+#endif
     pairing_front<K>(f, bad, mode, g1 ? g1 + 12 * e : nullptr, g1inf ? g1inf + e : nullptr, g2 ? g2 + 24 * e2 : nullptr,
-                     g2inf ? g2inf + e2 : nullptr, k, in12 ? in12 + 72 * i : nullptr, tab, tabinf, kf);
+                     g2inf ? g2inf + e2 : nullptr, k, in12 ? in12 + 72 * i : nullptr, tab, tabinf, kf, rs_ext);
     if (mode & ZKP_DO_FINAL_EXP) {
         FeState s;
         Fp nrm = fe_prepare(s, f);
@@ -81,11 +102,25 @@ cudaError_t zkp_launch_k_pairing(int mode, const uint64_t *g1, const uint8_t *g1
     fs.norm = fs.lanes ? fs.lanes + 2 * n * ZKP_FE_LANE_FP : nullptr;
     fs.n2 = 2 * n;
     dim3 g((unsigned)((2 * n + ZKP_TPB - 1) / ZKP_TPB)), b(ZKP_TPB);
+#if ZKP_SMEM_STATE
+    static bool attr_done = false;   // (set once per process; the attribute is per function, not per device context, on one device type)
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_pairing<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZKP_SMEM_STRIDE(1) * ZKP_TPB);
+        cudaFuncSetAttribute(k_pairing<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_pairing<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_pairing<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_pairing<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        attr_done = true;
+    }
+#define ZKP_SM(K) (size_t)(ZKP_SMEM_STRIDE(K) * ZKP_TPB)
+#else
+#define ZKP_SM(K) 0
+#endif
     switch (pair_capacity(k)) {
-        case 1: k_pairing<1><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
-        case 2: k_pairing<2><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
-        case 4: k_pairing<4><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
-        default: k_pairing<8><<<g, b, 0, st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
+        case 1: k_pairing<1><<<g, b, ZKP_SM(1), st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
+        case 2: k_pairing<2><<<g, b, ZKP_SM(2), st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
+        case 4: k_pairing<4><<<g, b, ZKP_SM(4), st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
+        default: k_pairing<8><<<g, b, ZKP_SM(8), st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
     }
     *launches = 1;
     if (mode & ZKP_DO_FINAL_EXP) {
