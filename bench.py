@@ -464,17 +464,13 @@ def bench_product(eng, z, sharding, torch, dist, world, rank, dev, st, n, seed, 
     ml = out[:nc4]
     scratch = torch.empty(eng.product_scratch_elems(nc4) * 72, dtype=torch.int64, device=dev)
     partial = torch.empty(72, dtype=torch.int64, device=dev)
-    gathered = torch.empty((world, 72), dtype=torch.int64, device=dev)
     gt = torch.empty((1, 72), dtype=torch.int64, device=dev)
     prod = [None]
 
     def one_product():
         eng.pairing_dev(z.MODE_MILLER, ml, g1=g1, g2=g2, n_checks=nc4, pairs_per_check=4, err=err, stream=st)
         eng.fp12_product_dev(ml, nc4, scratch, partial, err=err, stream=st)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), partial)      # NCCL, on the current (launching) stream
-        else:
-            gathered[0].copy_(partial)
+        gathered = sharding.gather_partials(partial, world)             # NCCL all_gather, ordered with the launching stream
         prod[0] = _fold_partials(eng, torch, dev, st, gathered)
         eng.pairing_dev(z.MODE_FINAL_EXP, gt, in_fp12=prod[0].view(1, 72), n_checks=1, err=err, stream=st)
 
@@ -558,9 +554,7 @@ def bench_sliced(eng, z, sharding, torch, dist, world, rank, dev, st, total, see
             return r
 
         def gather_fold(partial):
-            g = torch.empty((world, 72), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(g.view(-1), partial)
-            return _fold_partials(eng, torch, dev, st, g)
+            return _fold_partials(eng, torch, dev, st, sharding.gather_partials(partial, world))
 
         gt_checksum = gather_fold(fold(out, m))                      # product of all 2^24 Gt outputs
         nc4 = m // 4

@@ -107,11 +107,13 @@ def test_op_widths():
 @pytest.fixture(scope="module")
 def sim():
     d = os.path.join(ROOT, "tests", "host_sim")
-    so = os.path.join(d, "libzkpair_sim.so")
+    # ZKP_SIM_DEFINES="-DNAME ..." runs the same tests against a build variant of the device headers
+    defs = os.environ.get("ZKP_SIM_DEFINES", "").split()
+    so = os.path.join(d, "libzkpair_sim%s.so" % ("_" + re.sub(r"\W+", "_", "".join(defs)) if defs else ""))
     src = [os.path.join(d, "sim.cpp")] + [os.path.join(ROOT, "zkvm_pairings_b200", "csrc", f)
                                           for f in ("fp.cuh", "tower.cuh", "pairing.cuh", "ops.cuh", "consts.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src[0]])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared"] + defs + ["-o", so, src[0]])
     return ctypes.CDLL(so)
 
 

@@ -1,6 +1,8 @@
 """The N > 1 path on CPU (gloo, world_size 2): the contiguous-slice partition, the max-over-ranks
 timing reduction bench.py uses, and the reference arm under torchrun (rank 0 alone prints one JSON
-line).  The GPU side of the same path is exercised by tests/test_gpu_parity.py on multi-GPU boxes."""
+line).  The GPU side of the same path: tests/test_gpu_parity.py::test_multi_device_context_matches_single_device
+and ::test_config5_sharded_2p24_with_product_gather (skipped on single-GPU boxes; `gpurun --gpus 2`), and
+bench.py's `product` / `config5` / `strong` records under torchrun (NCCL all_gather of the Fp12 partials)."""
 import json
 import os
 import socket
@@ -48,6 +50,50 @@ def test_slices_and_max_reduction_world_size_2():
     assert (lo0, hi0, lo1, hi1) == (0, 500, 500, 1001)                    # contiguous, disjoint, covering
     assert m0 == m1 == 107.0                                              # both ranks see the slowest time
     assert abs(rate0 - 2 * 500 * 3 / 0.107) < 1e-6 and f1 == 1 << 20 and f0 == 0
+
+
+def _product_worker(rank, world, port, n, q):
+    """One rank of a sharded product with the ORACLE standing in for the GPU: Miller product of its slice, gather of
+    the 576-byte partials (gloo), product of the partials, one final exponentiation."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import coracle
+    import util
+    from zkvm_pairings_b200 import sharding
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g1, i1, g2, i2 = util.oracle_points(coracle, 0xA11, 0, n)
+    i1[1] = 1
+    lo, hi = sharding.slice_bounds(n, world, rank)
+    ml, _ = coracle.miller_product(g1[lo:hi], i1[lo:hi], g2[lo:hi], i2[lo:hi])
+    parts = sharding.gather_partials(torch.from_numpy(ml.view(np.int64)), world).numpy().view(np.uint64)
+    acc = parts[0]
+    for r in range(1, world):
+        acc = coracle.tower_op("fp12_mul", acc[None], parts[r][None])[0]
+    gt = coracle.final_exp_batch(acc[None])[0]
+    eml, egt = coracle.miller_product(g1, i1, g2, i2)
+    q.put((rank, bool(np.array_equal(acc, eml)), bool(np.array_equal(gt, egt)), bool(np.array_equal(parts[rank], ml))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_product_partial_gather_world_size_2():
+    """SURVEY 8e's one exchange step on CPU: contiguous slices, all_gather of the Fp12 partials, product, one final
+    exponentiation -- bit-identical to the unsharded product on every rank (uneven split: 7 pairs over 2 ranks)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q, port, world = ctx.Queue(), _free_port(), 2
+    procs = [ctx.Process(target=_product_worker, args=(r, world, port, 7, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True, True, True), (1, True, True, True)]
 
 
 def test_slice_bounds_cover_every_partition():

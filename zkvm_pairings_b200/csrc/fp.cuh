@@ -203,6 +203,20 @@ ZKP_HD Fp fp_sub(const Fp &a, const Fp &b) {
     d.l[0] = sub_cc(a.l[0], b.l[0]);
 #pragma unroll
     for (int i = 1; i < ZKP_NL; i++) d.l[i] = subc_cc(a.l[i], b.l[i]);
+#if defined(ZKP_SUB_NOBRANCH)
+    // branch-free: d + 2p is formed unconditionally, one limb behind the subtraction chain (ptxas overlaps the two
+    // carry chains), and selected by the borrow -- no BSSY / BRA / BSYNC around a second serial chain
+    bool neg = subc(0, 0) != 0;
+    Fp e;
+    e.l[0] = add_cc(d.l[0], ZKP_2P[0]);
+#pragma unroll
+    for (int i = 1; i < ZKP_NL - 1; i++) e.l[i] = addc_cc(d.l[i], ZKP_2P[i]);
+    e.l[ZKP_NL - 1] = addc(d.l[ZKP_NL - 1], ZKP_2P[ZKP_NL - 1]);
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < ZKP_NL; i++) r.l[i] = neg ? e.l[i] : d.l[i];
+    return r;
+#else
     if (subc(0, 0) != 0) {   // a < b: add 2p back (a short predicated carry chain, no selects)
         d.l[0] = add_cc(d.l[0], ZKP_2P[0]);
 #pragma unroll
@@ -210,6 +224,7 @@ ZKP_HD Fp fp_sub(const Fp &a, const Fp &b) {
         d.l[ZKP_NL - 1] = addc(d.l[ZKP_NL - 1], ZKP_2P[ZKP_NL - 1]);
     }
     return d;
+#endif
 }
 // -a = 2p - a, in [0, 2p]                    -- src/fp.rs:381-405
 ZKP_HD Fp fp_neg(const Fp &a) {

@@ -196,7 +196,7 @@ enum { ZKP_DO_MILLER = 1, ZKP_DO_FINAL_EXP = 2 };
 template <int K>
 ZKP_HD void pairing_front(Fp12 &f, bool &bad, int mode, const uint64_t *g1, const uint8_t *g1inf, const uint64_t *g2,
                           const uint8_t *g2inf, int k, const uint64_t *in12, const Fp *tab = nullptr,
-                          const uint8_t *tabinf = nullptr, int kf = 0, G2P *rs_ext = nullptr) {
+                          const uint8_t *tabinf = nullptr, int kf = 0, G2P *rs_ext = nullptr, Fp6 *tmp = nullptr) {
     // k pairs in total; the last kf of them take their G2 lines from the prepared tables `tab`
     // (then g2 / g2inf hold only the k - kf per-check points)
     if (mode & ZKP_DO_MILLER) {
@@ -215,7 +215,11 @@ ZKP_HD void pairing_front(Fp12 &f, bool &bad, int mode, const uint64_t *g1, cons
             skip[j] = skip[j] | (g2inf && g2inf[j]);
         }
         for (int j = 0; j < kf; j++) skip[kv + j] = skip[kv + j] | (tabinf && tabinf[j]);
-        miller_loop(f, ps, qs, skip, rs, kv, tab, kf);
+#ifdef ZKP_INPLACE12
+        Fp6 tmp_local;   // the one Fp6 temporary of the in-place Fp12 operations when the caller does not supply one
+        if (!tmp) tmp = &tmp_local;
+#endif
+        miller_loop(f, ps, qs, skip, rs, kv, tab, kf, tmp);
     } else {
         load_fp12(f, in12, bad);
     }

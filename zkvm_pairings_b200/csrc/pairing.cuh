@@ -72,7 +72,7 @@ ZKP_NOINLINE void addition_step(G2P &r, const G2A &q, Fp2 *co) {
 // lanes of a warp stay on one path.
 ZKP_HD Fp2 fp2_select(bool c, const Fp2 &a, const Fp2 &b) { Fp2 r; r.c = fp_select(c, a.c, b.c); return r; }
 // `first`: f is still one (the very first line of the loop), so the product is the line itself.
-ZKP_HD void ell(Fp12 &f, const Fp2 *co, const G1A &p, bool skip, bool first = false) {
+ZKP_HD void ell(Fp12 &f, const Fp2 *co, const G1A &p, bool skip, bool first = false, Fp6 *tmp = nullptr) {
     Fp2 a = fp2_select(skip, fp2_zero(), fp2_mul_fp(co[0], p.y));
     Fp2 b = fp2_select(skip, fp2_zero(), fp2_mul_fp(co[1], p.x));
     Fp2 c = fp2_select(skip, fp2_one(), co[2]);
@@ -81,6 +81,9 @@ ZKP_HD void ell(Fp12 &f, const Fp2 *co, const G1A &p, bool skip, bool first = fa
         f.c0.c1 = b;
         f.c1.c1 = a;
     } else {
+#ifdef ZKP_INPLACE12
+        if (tmp) { fp12_mul_by_014_inplace(f, *tmp, c, b, a); return; }
+#endif
         fp12_mul_by_014(f, c, b, a);
     }
 }
@@ -104,7 +107,7 @@ ZKP_HD Fp2 line_tab_load(const Fp *tab, int point, int step, int c) {
 // pairs bring their own G2 point (qs, scratch rs), the last kf use prepared line tables.  Pairs
 // flagged `skip` (a point at infinity) contribute one.  Output is conjugated (x < 0).
 ZKP_HD void miller_loop(Fp12 &f, const G1A *ps, const G2A *qs, const bool *skip, G2P *rs, int kv,
-                        const Fp *tab = nullptr, int kf = 0) {
+                        const Fp *tab = nullptr, int kf = 0, Fp6 *tmp = nullptr) {
     Fp2 co[3];
     fp12_set_one(f);
     for (int j = 0; j < kv; j++) {
@@ -119,26 +122,29 @@ ZKP_HD void miller_loop(Fp12 &f, const G1A *ps, const G2A *qs, const bool *skip,
         ZKP_CODE_SYNC(1);
         for (int j = 0; j < kv; j++) {
             doubling_step(rs[j], co);
-            ell(f, co, ps[j], skip[j], step == 0 && j == 0);
+            ell(f, co, ps[j], skip[j], step == 0 && j == 0, tmp);
         }
         for (int j = 0; j < kf; j++) {
             for (int c = 0; c < 3; c++) co[c] = line_tab_load(tab, j, step, c);
-            ell(f, co, ps[kv + j], skip[kv + j], step == 0 && kv == 0 && j == 0);
+            ell(f, co, ps[kv + j], skip[kv + j], step == 0 && kv == 0 && j == 0, tmp);
         }
         step++;
         if (bit) {
             ZKP_CODE_SYNC(2);
             for (int j = 0; j < kv; j++) {
                 addition_step(rs[j], qs[j], co);
-                ell(f, co, ps[j], skip[j]);
+                ell(f, co, ps[j], skip[j], false, tmp);
             }
             for (int j = 0; j < kf; j++) {
                 for (int c = 0; c < 3; c++) co[c] = line_tab_load(tab, j, step, c);
-                ell(f, co, ps[kv + j], skip[kv + j]);
+                ell(f, co, ps[kv + j], skip[kv + j], false, tmp);
             }
             step++;
         }
         ZKP_CODE_SYNC(2);
+#ifdef ZKP_INPLACE12
+        if (b >= 0 && tmp) { fp12_sqr_inplace(f, *tmp); continue; }
+#endif
         if (b >= 0) fp12_sqr(f, f);
     }
     fp12_conj(f, f);

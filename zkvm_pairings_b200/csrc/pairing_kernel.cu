@@ -4,6 +4,8 @@
 // full-mask SHFLs instead of the match/vote-guarded pair-masked ones the divergent kernels need.
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #define ZKP_CONVERGED 1
 #define zkp zkp_conv   // this unit's own copy of the device functions (kernels.cu holds the pair-masked one)
 // Block-wide rendezvous points (ZKP_CODE_SYNC, fp.cuh) at the entry of every Fp6-level body, and with them FOUR
@@ -39,8 +41,9 @@ using namespace zkp;
 #ifndef ZKP_SMEM_STATE
 #define ZKP_SMEM_STATE 2
 #endif
-// bytes of shared memory per thread: 304 = 76 words (f + 16 pad), 432 = 108 words (f + R); both are 12 mod 32 words
-#define ZKP_SMEM_STRIDE(K) (((K) == 1 && ZKP_SMEM_STATE >= 2) ? 432 : 304)
+// (3 = f and the one Fp6 temporary of the in-place Fp12 operations, needs ZKP_INPLACE12; R thread-local)
+// bytes of shared memory per thread: 304 = 76 words (f + 16 pad), 432 = 108 words (f + R or f + T); both are 12 mod 32 words
+#define ZKP_SMEM_STRIDE(K) ((ZKP_SMEM_STATE >= 3 || ((K) == 1 && ZKP_SMEM_STATE == 2)) ? 432 : 304)
 
 // mode: bit0 Miller loop, bit1 first half of the final exponentiation.  One lane pair per check of
 // k (<= K) pairs.  Without bit1 the Miller output is stored canonically to `out`.
@@ -62,13 +65,15 @@ k_pairing(int mode, const uint64_t *__restrict__ g1, const uint8_t *__restrict__
     extern __shared__ uint4 zkp_smem[];
     char *slice = reinterpret_cast<char *>(zkp_smem) + (size_t)threadIdx.x * ZKP_SMEM_STRIDE(K);
     Fp12 &f = *reinterpret_cast<Fp12 *>(slice);
-    G2P *rs_ext = (K == 1 && ZKP_SMEM_STATE >= 2) ? reinterpret_cast<G2P *>(slice + sizeof(Fp12)) : nullptr;
+    G2P *rs_ext = (K == 1 && ZKP_SMEM_STATE == 2) ? reinterpret_cast<G2P *>(slice + sizeof(Fp12)) : nullptr;
+    Fp6 *tmp_ext = ZKP_SMEM_STATE >= 3 ? reinterpret_cast<Fp6 *>(slice + sizeof(Fp12)) : nullptr;
 #else
     Fp12 f;
     G2P *rs_ext = nullptr;
+    Fp6 *tmp_ext = nullptr;
 #endif
     pairing_front<K>(f, bad, mode, g1 ? g1 + 12 * e : nullptr, g1inf ? g1inf + e : nullptr, g2 ? g2 + 24 * e2 : nullptr,
-                     g2inf ? g2inf + e2 : nullptr, k, in12 ? in12 + 72 * i : nullptr, tab, tabinf, kf, rs_ext);
+                     g2inf ? g2inf + e2 : nullptr, k, in12 ? in12 + 72 * i : nullptr, tab, tabinf, kf, rs_ext, tmp_ext);
     if (mode & ZKP_DO_FINAL_EXP) {
         FeState s;
         Fp nrm = fe_prepare(s, f);
@@ -103,14 +108,21 @@ cudaError_t zkp_launch_k_pairing(int mode, const uint64_t *g1, const uint8_t *g1
     fs.n2 = 2 * n;
     dim3 g((unsigned)((2 * n + ZKP_TPB - 1) / ZKP_TPB)), b(ZKP_TPB);
 #if ZKP_SMEM_STATE
-    static bool attr_done = false;   // (set once per process; the attribute is per function, not per device context, on one device type)
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_pairing<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZKP_SMEM_STRIDE(1) * ZKP_TPB);
+    // function attributes are per DEVICE: opt in to > 48 KB of dynamic shared memory once on each device that launches
+    static std::atomic<unsigned long long> attr_done{0};
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (!((attr_done.load() >> (cur & 63)) & 1ull)) {
+        cudaError_t e = cudaFuncSetAttribute(k_pairing<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZKP_SMEM_STRIDE(1) * ZKP_TPB);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pairing<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZKP_SMEM_STRIDE(2) * ZKP_TPB);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pairing<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZKP_SMEM_STRIDE(4) * ZKP_TPB);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pairing<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZKP_SMEM_STRIDE(8) * ZKP_TPB);
+        if (e != cudaSuccess) return e;
         cudaFuncSetAttribute(k_pairing<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         cudaFuncSetAttribute(k_pairing<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         cudaFuncSetAttribute(k_pairing<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         cudaFuncSetAttribute(k_pairing<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        attr_done = true;
+        attr_done.fetch_or(1ull << (cur & 63));
     }
 #define ZKP_SM(K) (size_t)(ZKP_SMEM_STRIDE(K) * ZKP_TPB)
 #else

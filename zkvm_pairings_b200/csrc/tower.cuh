@@ -330,6 +330,67 @@ ZKP_NOINLINE void fp12_sqr(Fp12 &r, const Fp12 &a) {
     fp6_sub(t, t, ab);
     r.c0 = t;
 }
+#ifdef ZKP_INPLACE12
+// In-place forms of the two Fp12 operations of the Miller loop: ONE Fp6 temporary (handed in by the caller, so that
+// it can live in shared memory next to f) instead of three thread-local ones each; same field elements.
+// (a0 + a1)(a0 + v a1) with the operand sums formed on the fly; r may alias a0 or a1
+ZKP_NOINLINE void fp6_mul_sums(Fp6 &r, const Fp6 &a0, const Fp6 &a1) {
+    ZKP_CODE_SYNC(4);
+    Fp2 v0 = fp2_mul(fp2_add(a0.c0, a1.c0), fp2_add(a0.c0, fp2_mul_nr(a1.c2)));
+    Fp2 v1 = fp2_mul(fp2_add(a0.c1, a1.c1), fp2_add(a0.c1, a1.c0));
+    Fp2 v2 = fp2_mul(fp2_add(a0.c2, a1.c2), fp2_add(a0.c2, a1.c1));
+    Fp2 t0, t1, t2;
+    {
+        Fp2 s1 = fp2_add(a0.c1, a1.c1), s2 = fp2_add(a0.c2, a1.c2);
+        Fp2 u1 = fp2_add(a0.c1, a1.c0), u2 = fp2_add(a0.c2, a1.c1);
+        t0 = fp2_sub(fp2_sub(fp2_mul(fp2_add(s1, s2), fp2_add(u1, u2)), v1), v2);
+    }
+    {
+        Fp2 s0 = fp2_add(a0.c0, a1.c0), s1 = fp2_add(a0.c1, a1.c1);
+        Fp2 u0 = fp2_add(a0.c0, fp2_mul_nr(a1.c2)), u1 = fp2_add(a0.c1, a1.c0);
+        t1 = fp2_sub(fp2_sub(fp2_mul(fp2_add(s0, s1), fp2_add(u0, u1)), v0), v1);
+    }
+    {
+        Fp2 s0 = fp2_add(a0.c0, a1.c0), s2 = fp2_add(a0.c2, a1.c2);
+        Fp2 u0 = fp2_add(a0.c0, fp2_mul_nr(a1.c2)), u2 = fp2_add(a0.c2, a1.c1);
+        t2 = fp2_sub(fp2_sub(fp2_mul(fp2_add(s0, s2), fp2_add(u0, u2)), v0), v2);
+    }
+    r.c0 = fp2_add(v0, fp2_mul_nr(t0));
+    r.c1 = fp2_add(t1, fp2_mul_nr(v2));
+    r.c2 = fp2_add(t2, v1);
+}
+// f <- f^2 (complex squaring, src/fp12.rs:173-184): T = c0 c1; c0 <- (c0 + c1)(c0 + v c1) - T - v T; c1 <- 2 T
+ZKP_NOINLINE void fp12_sqr_inplace(Fp12 &f, Fp6 &T) {
+    fp6_mul(T, f.c0, f.c1);
+    fp6_mul_sums(f.c0, f.c0, f.c1);
+    f.c1.c0 = fp2_dbl(T.c0);
+    f.c1.c1 = fp2_dbl(T.c1);
+    f.c1.c2 = fp2_dbl(T.c2);
+    f.c0.c0 = fp2_sub(fp2_sub(f.c0.c0, T.c0), fp2_mul_nr(T.c2));
+    f.c0.c1 = fp2_sub(fp2_sub(f.c0.c1, T.c1), T.c0);
+    f.c0.c2 = fp2_sub(fp2_sub(f.c0.c2, T.c2), T.c1);
+}
+// f <- f * (c0 + c1 v + c4 v w) (src/fp12.rs:99-111): T = (f.c0 + f.c1)(c0, c1 + c4); f.c0 <- aa; f.c1 <- bb; combine
+ZKP_NOINLINE void fp12_mul_by_014_inplace(Fp12 &f, Fp6 &T, const Fp2 &c0, const Fp2 &c1, const Fp2 &c4) {
+    fp6_add(T, f.c1, f.c0);
+    fp6_mul_by_01(T, T, c0, fp2_add(c1, c4));
+    fp6_mul_by_01(f.c0, f.c0, c0, c1);          // aa
+    fp6_mul_by_1(f.c1, f.c1, c4);               // bb
+    Fp2 a, b;
+    a = f.c0.c0; b = f.c1.c0;
+    f.c0.c0 = fp2_add(a, fp2_mul_nr(f.c1.c2));
+    Fp2 n10 = fp2_sub(fp2_sub(T.c0, a), b);
+    a = f.c0.c1;
+    f.c0.c1 = fp2_add(a, b);
+    Fp2 b1 = f.c1.c1;
+    Fp2 n11 = fp2_sub(fp2_sub(T.c1, a), b1);
+    a = f.c0.c2;
+    f.c0.c2 = fp2_add(a, b1);
+    f.c1.c2 = fp2_sub(fp2_sub(T.c2, a), f.c1.c2);
+    f.c1.c0 = n10;
+    f.c1.c1 = n11;
+}
+#endif
 // f * (c0 + c1 v + c4 v w): sparse line multiplication  -- src/fp12.rs:99-111 ; in place
 ZKP_NOINLINE void fp12_mul_by_014(Fp12 &f, const Fp2 &c0, const Fp2 &c1, const Fp2 &c4) {
     Fp6 aa, bb, t;
