@@ -10,3 +10,4 @@ python bench.py --steps 5 --warmup 3 > gpurun_out/r2c_bench.json 2> gpurun_out/r
 python -c "
 import json; d=json.load(open('gpurun_out/r2c_bench.json')); print(d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['executed_frac'], d['roofline']['peak'])
 print({k:v['value'] for k,v in d['configs'].items()}, d['product']['value'])"
+./build/dfma_probe > gpurun_out/r2c_dfma_probe.txt 2>&1; cat gpurun_out/r2c_dfma_probe.txt
