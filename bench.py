@@ -468,7 +468,7 @@ def bench_product(eng, z, sharding, torch, dist, world, rank, dev, st, n, seed, 
     prod = [None]
 
     def one_product():
-        eng.pairing_dev(z.MODE_MILLER, ml, g1=g1, g2=g2, n_checks=nc4, pairs_per_check=4, err=err, stream=st)
+        eng.pairing_dev(z.MODE_MILLER_FOR_FINAL_EXP, ml, g1=g1, g2=g2, n_checks=nc4, pairs_per_check=4, err=err, stream=st)
         eng.fp12_product_dev(ml, nc4, scratch, partial, err=err, stream=st)
         gathered = sharding.gather_partials(partial, world)             # NCCL all_gather, ordered with the launching stream
         prod[0] = _fold_partials(eng, torch, dev, st, gathered)
@@ -508,7 +508,9 @@ def bench_product(eng, z, sharding, torch, dist, world, rank, dev, st, n, seed, 
         vgt = torch.empty((1, 72), dtype=torch.int64, device=dev)
         eng.pairing_dev(z.MODE_FINAL_EXP, vgt, in_fp12=acc.view(1, 72), n_checks=1, err=err, stream=st)
         torch.cuda.synchronize()
-        matches = bool(torch.equal(acc, prod[0])) and bool(torch.equal(vgt[0], result_gt))
+        # (the timed path runs the Miller loops with free line scaling, so its un-exponentiated product differs from this
+        # one by a subfield factor; the Gt values must be bit-identical)
+        matches = bool(torch.equal(vgt[0], result_gt))
         assert matches, "sharded product differs from the single-GPU product"
     barrier()
     total = world * n
@@ -560,11 +562,11 @@ def bench_sliced(eng, z, sharding, torch, dist, world, rank, dev, st, total, see
         nc4 = m // 4
         barrier()
         e0.record()
-        eng.pairing_dev(z.MODE_MILLER, out[:nc4], g1=g1, g2=g2, n_checks=nc4, pairs_per_check=4, err=err, stream=st)
+        eng.pairing_dev(z.MODE_MILLER_FOR_FINAL_EXP, out[:nc4], g1=g1, g2=g2, n_checks=nc4, pairs_per_check=4, err=err, stream=st)
         part = fold(out[:nc4], nc4)
         if m % 4:
             tail = torch.empty((m % 4, 72), dtype=torch.int64, device=dev)
-            eng.pairing_dev(z.MODE_MILLER, tail, g1=g1[4 * nc4:], g2=g2[4 * nc4:], err=err, stream=st)
+            eng.pairing_dev(z.MODE_MILLER_FOR_FINAL_EXP, tail, g1=g1[4 * nc4:], g2=g2[4 * nc4:], err=err, stream=st)
             part = _fold_partials(eng, torch, dev, st, torch.cat([part.view(1, 72), tail]))
         prod = gather_fold(part)
         gt = torch.empty((1, 72), dtype=torch.int64, device=dev)

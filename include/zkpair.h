@@ -152,14 +152,18 @@ int32_t zkp_multi_pairing_batch(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8
 /* prod_i e(G1[i], G2[i]) for one large product: per-device shared-accumulator Miller loops (four pairs per
  * loop) over a contiguous slice, streamed in double-buffered chunks, per-device Fp12 partial product, gather
  * of the 576-byte partials to the first device, multiply, ONE final exponentiation.  out_miller_product
- * (optional) receives the un-exponentiated product (a field element: independent of the grouping). */
+ * (optional) receives the un-exponentiated product in SURVEY 9.1's line scaling (a field element: independent of the
+ * grouping and of the number of devices); with out_miller_product == NULL the cheaper line steps are used. */
 int32_t zkp_multi_miller_product(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_inf,
                                  const uint64_t *g2_xy, const uint8_t *g2_inf, size_t n,
                                  uint64_t *out_miller_product, uint64_t *out_gt);
 
 /* ---- device-resident entry points (asynchronous; pointers are device pointers on `dev`) ---- */
 
-/* mode: 1 = Miller loop only, 2 = final exponentiation only (d_in_fp12 -> d_out), 3 = pairing.
+/* mode: 1 = Miller loop only, 2 = final exponentiation only (d_in_fp12 -> d_out), 3 = pairing, 5 = Miller loop whose
+ * output is only meant for a later final exponentiation (or for products of such outputs): it equals the mode-1 value up
+ * to a factor from a proper subfield, which the final exponentiation removes -- the cheaper homogeneous line steps the
+ * fused pairing path uses (mode 3 == mode 2 after mode 1 == mode 2 after mode 5, bit for bit).
  * d_err (optional): device uint32_t that is OR-ed with 1 when an input is non-canonical. */
 int32_t zkp_pairing_dev(zkp_ctx *ctx, int32_t dev, int32_t mode, const uint64_t *d_g1_xy,
                         const uint8_t *d_g1_inf, const uint64_t *d_g2_xy, const uint8_t *d_g2_inf,

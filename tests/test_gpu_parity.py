@@ -458,6 +458,34 @@ def test_multi_miller_product_grouping_and_chunks(engine, coracle):
         torch.cuda.synchronize()
         assert np.array_equal(d_out.cpu().numpy().view(np.uint64), prod), n
         assert np.array_equal(engine.final_exponentiation_batch(prod[None])[0], gt), n
+        # Gt only: the Miller loops run with free line scaling (cheaper homogeneous line steps), same Gt bit for bit
+        none, gt_only = engine.multi_miller_product(g1, g2, i1, i2, want_miller_product=False)
+        assert none is None and np.array_equal(gt_only, gt), n
+
+
+def test_miller_mode_with_free_line_scaling(engine, coracle):
+    """mode 5 (Miller loop whose output only feeds a final exponentiation): differs from SURVEY 9.1's Miller value
+    by a subfield factor, gives the same Gt bit for bit, alone and inside shared-accumulator checks."""
+    import torch
+    import zkvm_pairings_b200 as z
+    n, k = 512, 4
+    g1, i1, g2, i2 = util.oracle_points(coracle, 555, 0, n)
+    st = torch.cuda.current_stream().cuda_stream
+    dg1, dg2 = torch.from_numpy(g1.view(np.int64)).cuda(), torch.from_numpy(g2.view(np.int64)).cuda()
+    for kk in (1, k):
+        nc = n // kk
+        m5 = torch.empty((nc, 72), dtype=torch.int64, device="cuda")
+        gt = torch.empty((nc, 72), dtype=torch.int64, device="cuda")
+        engine.pairing_dev(z.MODE_MILLER_FOR_FINAL_EXP, m5, g1=dg1, g2=dg2, n_checks=nc, pairs_per_check=kk, stream=st)
+        engine.pairing_dev(z.MODE_FINAL_EXP, gt, in_fp12=m5, n_checks=nc, stream=st)
+        torch.cuda.synchronize()
+        exp, _ = coracle.multi_pairing_batch(g1, None, g2, None, kk)
+        assert np.array_equal(gt.cpu().numpy().view(np.uint64), exp)
+        m1 = coracle.multi_miller_batch(g1, None, g2, None, kk)
+        assert not np.array_equal(m5.cpu().numpy().view(np.uint64), m1)      # a different representative ...
+    from zkvm_pairings_b200 import ZkpError
+    with pytest.raises(ZkpError):
+        engine.pairing_dev(4, gt, g1=dg1, g2=dg2, stream=st)
 
 
 def test_default_stream_ordering_and_device_restored(engine, coracle):

@@ -545,7 +545,7 @@ int32_t zkp_pairing_dev(zkp_ctx *ctx, int32_t dev, int32_t mode, const uint64_t 
                         const uint64_t *d_in_fp12, uint64_t *d_out, uint8_t *d_is_one, uint32_t *d_err, void *stream) {
     int32_t rc = check_dev(ctx, dev);
     if (rc) return rc;
-    if (mode < 1 || mode > 3 || !d_out) return fail(ZKP_ERR_INVALID_ARG, "bad mode / NULL output");
+    if (!(mode == 1 || mode == 2 || mode == 3 || mode == 5) || !d_out) return fail(ZKP_ERR_INVALID_ARG, "bad mode / NULL output");
     if ((mode & 1) && (!d_g1_xy || !d_g2_xy || pairs_per_check < 1)) return fail(ZKP_ERR_INVALID_ARG, "NULL point buffers");
     if (!(mode & 1) && !d_in_fp12) return fail(ZKP_ERR_INVALID_ARG, "NULL Fp12 input");
     if (pairs_per_check > ZKP_MAX_PAIRS_PER_CHECK) return fail(ZKP_ERR_TOO_MANY_PAIRS, "pairs_per_check > 8");
@@ -630,6 +630,7 @@ struct HostJob {
     uint64_t *out = nullptr, *og1 = nullptr, *og2 = nullptr;
     uint8_t *flags = nullptr, *og1inf = nullptr, *og2inf = nullptr;
     int k = 1, op = 0;
+    int miller_mode = 1;   // mode 64: 1 = SURVEY 9.1 line scaling (the Miller product is returned), 5 = free scaling (only Gt is)
     uint64_t seed = 0, first = 0;
 };
 
@@ -776,11 +777,11 @@ static int32_t run_slice(zkp_ctx *ctx, DevState &d, const HostJob &j, size_t lo,
                 di2 = (const uint8_t *)B[B_G2INF].p;
             }
             if (nc4)
-                CUS(launch_pairing(ctx, d, 1, (const uint64_t *)B[B_G1].p, di1, (const uint64_t *)B[B_G2].p, di2, nc4, ZKP_PRODUCT_GROUP,
+                CUS(launch_pairing(ctx, d, j.miller_mode, (const uint64_t *)B[B_G1].p, di1, (const uint64_t *)B[B_G2].p, di2, nc4, ZKP_PRODUCT_GROUP,
                                    nullptr, (uint64_t *)B[B_OUT].p, nullptr, d.d_err, st));
             if (rem) {
                 size_t o = nc4 * ZKP_PRODUCT_GROUP;
-                CUS(launch_pairing(ctx, d, 1, (const uint64_t *)B[B_G1].p + 12 * o, di1 ? di1 + o : nullptr,
+                CUS(launch_pairing(ctx, d, j.miller_mode, (const uint64_t *)B[B_G1].p + 12 * o, di1 ? di1 + o : nullptr,
                                    (const uint64_t *)B[B_G2].p + 24 * o, di2 ? di2 + o : nullptr, 1, (int)rem, nullptr,
                                    (uint64_t *)B[B_OUT].p + 72 * nc4, nullptr, d.d_err, st));
             }
@@ -1091,6 +1092,7 @@ int32_t zkp_multi_miller_product(zkp_ctx *ctx, const uint64_t *g1, const uint8_t
     if (n < 2 * nd) nd = 1;
     HostJob j;
     j.mode = 64; j.g1 = g1; j.g1inf = g1inf; j.g2 = g2; j.g2inf = g2inf;
+    j.miller_mode = out_miller_product ? 1 : 5;   // the un-exponentiated product is only well defined with SURVEY 9.1's lines
     std::vector<int32_t> rcs(nd, ZKP_OK);
     std::vector<std::string> msgs(nd);
     if (nd == 1) {

@@ -186,7 +186,8 @@ ZKP_HD bool store_fp12(uint64_t *dst, const Fp12 &f, bool live = true) {
 ZKP_HD void load_fp12(Fp12 &f, const uint64_t *src, bool &bad) { load_fp2s(&f.c0.c0, src, 6, bad); }
 
 // mode bits for pairing_one
-enum { ZKP_DO_MILLER = 1, ZKP_DO_FINAL_EXP = 2 };
+// (ZKP_FREE_LINE_SCALING: the Miller output is only consumed by a later final exponentiation, so its lines may be scaled)
+enum { ZKP_DO_MILLER = 1, ZKP_DO_FINAL_EXP = 2, ZKP_FREE_LINE_SCALING = 4 };
 
 // One "check": k pairs -> shared-accumulator Miller loop (-> final exponentiation).  g1/g2/inf
 // point at this check's first pair.  Returns status bit0 = non-canonical input.  Control flow is
@@ -219,7 +220,12 @@ ZKP_HD void pairing_front(Fp12 &f, bool &bad, int mode, const uint64_t *g1, cons
         Fp6 tmp_local;   // the one Fp6 temporary of the in-place Fp12 operations when the caller does not supply one
         if (!tmp) tmp = &tmp_local;
 #endif
-        miller_loop(f, ps, qs, skip, rs, kv, tab, kf, tmp);
+#ifdef ZKP_NO_FUSED_LINES
+        const bool fused = false;
+#else
+        const bool fused = (mode & (ZKP_DO_FINAL_EXP | ZKP_FREE_LINE_SCALING)) != 0;   // only Gt is observable: line scaling is free (pairing.cuh)
+#endif
+        miller_loop(f, ps, qs, skip, rs, kv, tab, kf, tmp, fused);
     } else {
         load_fp12(f, in12, bad);
     }

@@ -67,6 +67,74 @@ ZKP_NOINLINE void addition_step(G2P &r, const G2A &q, Fp2 *co) {
     co[1] = fp2_dbl(fp2_neg(t6));
 }
 
+// ------------------------------------------------------------------ line steps of the FUSED pairing path
+//
+// SURVEY 9.1's line steps (above) fix the scaling of every line and with it the value of a Miller-loop output;
+// zkp_miller_loop_batch returns exactly that.  When the final exponentiation follows in the same call (pairing,
+// product checks) only Gt is observable, and Gt does not depend on how the lines are scaled by Fp2 factors
+// (the easy part kills every proper subfield), so that path uses the cheaper line steps in HOMOGENEOUS
+// projective coordinates (x = X/Z, y = Y/Z; Costello-Lange-Naehrig / Aranha et al. for y^2 = x^3 + b', b' = 4 xi):
+//   doubling  3 Fp2 mul + 6 Fp2 sqr (instead of 3 + 8):  A = XY/2, B = Y^2, C = Z^2, E = 3 b' C, F = 3E,
+//             X3 = A (B - F), Y3 = ((B + F)/2)^2 - 3 E^2, Z3 = B H with H = (Y + Z)^2 - B - C = 2YZ,
+//             tangent line  H yP - 3 X^2 xP + (B - E)
+//   addition  11 mul + 2 sqr:  theta = Y - y2 Z, lambda = X - x2 Z, C = theta^2, D = lambda^2, E = lambda D, F = Z C,
+//             G = X D, H = E + F - 2G, X3 = lambda H, Y3 = theta (G - H) - E Y, Z3 = Z E,
+//             chord  lambda yP - theta xP + (theta x2 - lambda y2)
+// The coefficient triple keeps the meaning of SURVEY 9.1's (c0, c1, c2) = (yP coefficient, xP coefficient, constant).
+// (a / 2) mod p for a 2p-redundant value: (a + p) / 2 when a is odd; a + p <= 3p < 2^384, result <= 1.5 p
+ZKP_HD Fp fp_half(const Fp &a) {
+    const uint32_t m = (a.l[0] & 1u) ? 0xffffffffu : 0u;
+    uint32_t t[ZKP_NL];
+    t[0] = add_cc(a.l[0], ZKP_P[0] & m);
+#pragma unroll
+    for (int i = 1; i < ZKP_NL - 1; i++) t[i] = addc_cc(a.l[i], ZKP_P[i] & m);
+    t[ZKP_NL - 1] = addc(a.l[ZKP_NL - 1], ZKP_P[ZKP_NL - 1] & m);
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < ZKP_NL - 1; i++) r.l[i] = (t[i] >> 1) | (t[i + 1] << 31);
+    r.l[ZKP_NL - 1] = t[ZKP_NL - 1] >> 1;
+    return r;
+}
+ZKP_HD Fp2 fp2_half(const Fp2 &a) { Fp2 r; r.c = fp_half(a.c); return r; }
+ZKP_HD Fp2 fp2_triple(const Fp2 &a) { return fp2_add(fp2_dbl(a), a); }
+
+ZKP_NOINLINE void doubling_step_h(G2P &r, Fp2 *co) {
+    ZKP_CODE_SYNC(4);
+    Fp2 A = fp2_half(fp2_mul(r.x, r.y));
+    Fp2 B = fp2_sqr(r.y);
+    Fp2 C = fp2_sqr(r.z);
+    Fp2 E = fp2_triple(fp2_mul_nr(C));
+    E = fp2_dbl(fp2_dbl(E));                               // 3 b' C = 12 xi C
+    Fp2 F = fp2_triple(E);
+    Fp2 X2 = fp2_sqr(r.x);
+    Fp2 H = fp2_sub(fp2_sqr(fp2_add(r.y, r.z)), fp2_add(B, C));
+    Fp2 G = fp2_half(fp2_add(B, F));
+    r.x = fp2_mul(A, fp2_sub(B, F));
+    r.y = fp2_sub(fp2_sqr(G), fp2_triple(fp2_sqr(E)));
+    r.z = fp2_mul(B, H);
+    co[0] = H;
+    co[1] = fp2_neg(fp2_triple(X2));
+    co[2] = fp2_sub(B, E);
+}
+ZKP_NOINLINE void addition_step_h(G2P &r, const G2A &q, Fp2 *co) {
+    ZKP_CODE_SYNC(4);
+    Fp2 th = fp2_sub(r.y, fp2_mul(q.y, r.z));
+    Fp2 la = fp2_sub(r.x, fp2_mul(q.x, r.z));
+    Fp2 C = fp2_sqr(th);
+    Fp2 D = fp2_sqr(la);
+    Fp2 E = fp2_mul(la, D);
+    Fp2 F = fp2_mul(r.z, C);
+    Fp2 G = fp2_mul(r.x, D);
+    Fp2 H = fp2_sub(fp2_add(E, F), fp2_dbl(G));
+    Fp2 yn = fp2_sub(fp2_mul(th, fp2_sub(G, H)), fp2_mul(E, r.y));
+    r.x = fp2_mul(la, H);
+    r.y = yn;
+    r.z = fp2_mul(r.z, E);
+    co[0] = la;
+    co[1] = fp2_neg(th);
+    co[2] = fp2_sub(fp2_mul(th, q.x), fp2_mul(la, q.y));
+}
+
 // SURVEY 9.1 ell: scale the line by P and fold it into f.  A pair flagged `skip` (a point at
 // infinity) multiplies f by the line (1, 0, 0) = one instead -- by selects, not by a branch, so all
 // lanes of a warp stay on one path.
@@ -106,8 +174,9 @@ ZKP_HD Fp2 line_tab_load(const Fp *tab, int point, int step, int c) {
 // Miller loop over kv + kf pairs sharing the accumulator f (one pair: single pairing).  The first kv
 // pairs bring their own G2 point (qs, scratch rs), the last kf use prepared line tables.  Pairs
 // flagged `skip` (a point at infinity) contribute one.  Output is conjugated (x < 0).
+// `fused`: the final exponentiation follows in the same call, so the cheaper homogeneous line steps may be used.
 ZKP_HD void miller_loop(Fp12 &f, const G1A *ps, const G2A *qs, const bool *skip, G2P *rs, int kv,
-                        const Fp *tab = nullptr, int kf = 0, Fp6 *tmp = nullptr) {
+                        const Fp *tab = nullptr, int kf = 0, Fp6 *tmp = nullptr, bool fused = false) {
     Fp2 co[3];
     fp12_set_one(f);
     for (int j = 0; j < kv; j++) {
@@ -121,7 +190,8 @@ ZKP_HD void miller_loop(Fp12 &f, const G1A *ps, const G2A *qs, const bool *skip,
         bool bit = b >= 0 && ((ZKP_X_HALF >> b) & 1);
         ZKP_CODE_SYNC(1);
         for (int j = 0; j < kv; j++) {
-            doubling_step(rs[j], co);
+            if (fused) doubling_step_h(rs[j], co);
+            else doubling_step(rs[j], co);
             ell(f, co, ps[j], skip[j], step == 0 && j == 0, tmp);
         }
         for (int j = 0; j < kf; j++) {
@@ -132,7 +202,8 @@ ZKP_HD void miller_loop(Fp12 &f, const G1A *ps, const G2A *qs, const bool *skip,
         if (bit) {
             ZKP_CODE_SYNC(2);
             for (int j = 0; j < kv; j++) {
-                addition_step(rs[j], qs[j], co);
+                if (fused) addition_step_h(rs[j], qs[j], co);
+                else addition_step(rs[j], qs[j], co);
                 ell(f, co, ps[j], skip[j], false, tmp);
             }
             for (int j = 0; j < kf; j++) {

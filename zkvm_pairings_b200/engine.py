@@ -31,6 +31,7 @@ _B_WIDTH = {"fp6_mul_by_1": 2, "fp6_mul_by_01": 4, "fp12_mul_by_014": 6, "fp_pow
 _BINARY = {"add", "sub", "mul"}
 
 MODE_MILLER, MODE_FINAL_EXP, MODE_PAIRING = 1, 2, 3
+MODE_MILLER_FOR_FINAL_EXP = 5   # Miller loop whose output only feeds a final exponentiation (free line scaling, cheaper)
 
 
 class ZkpError(RuntimeError):
@@ -211,10 +212,11 @@ class PairingEngine:
                                                       _ptr(out), _ptr(is_one)))
         return out, is_one
 
-    def multi_miller_product(self, g1, g2, g1_inf=None, g2_inf=None):
-        """One product over ALL pairs (sharded over the devices) -> (miller_product (72,), gt (72,))."""
+    def multi_miller_product(self, g1, g2, g1_inf=None, g2_inf=None, want_miller_product: bool = True):
+        """One product over ALL pairs (sharded over the devices) -> (miller_product (72,), gt (72,)).  With
+        ``want_miller_product=False`` only Gt is computed (-> (None, gt)) and the cheaper line steps are used."""
         g1, g2, i1, i2, n = self._points(g1, g2, g1_inf, g2_inf)
-        ml, gt = np.empty(72, dtype=np.uint64), np.empty(72, dtype=np.uint64)
+        ml, gt = (np.empty(72, dtype=np.uint64) if want_miller_product else None), np.empty(72, dtype=np.uint64)
         self._check(self._lib.zkp_multi_miller_product(self._ctx, _ptr(g1), _ptr(i1), _ptr(g2), _ptr(i2), n, _ptr(ml), _ptr(gt)))
         return ml, gt
 
