@@ -216,7 +216,7 @@ ZKP_HD void pairing_front(Fp12 &f, bool &bad, int mode, const uint64_t *g1, cons
             skip[j] = skip[j] | (g2inf && g2inf[j]);
         }
         for (int j = 0; j < kf; j++) skip[kv + j] = skip[kv + j] | (tabinf && tabinf[j]);
-#ifdef ZKP_INPLACE12
+#if ZKP_INPLACE12
         Fp6 tmp_local;   // the one Fp6 temporary of the in-place Fp12 operations when the caller does not supply one
         if (!tmp) tmp = &tmp_local;
 #endif

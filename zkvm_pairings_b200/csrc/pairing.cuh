@@ -149,7 +149,7 @@ ZKP_HD void ell(Fp12 &f, const Fp2 *co, const G1A &p, bool skip, bool first = fa
         f.c0.c1 = b;
         f.c1.c1 = a;
     } else {
-#ifdef ZKP_INPLACE12
+#if ZKP_INPLACE12
         if (tmp) { fp12_mul_by_014_inplace(f, *tmp, c, b, a); return; }
 #endif
         fp12_mul_by_014(f, c, b, a);
@@ -213,7 +213,7 @@ ZKP_HD void miller_loop(Fp12 &f, const G1A *ps, const G2A *qs, const bool *skip,
             step++;
         }
         ZKP_CODE_SYNC(2);
-#ifdef ZKP_INPLACE12
+#if ZKP_INPLACE12
         if (b >= 0 && tmp) { fp12_sqr_inplace(f, *tmp); continue; }
 #endif
         if (b >= 0) fp12_sqr(f, f);

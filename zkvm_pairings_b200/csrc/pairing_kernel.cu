@@ -38,8 +38,12 @@ using namespace zkp;
 // Measured (profiles/r2b_smem_state_variants.txt): Miller loop at 2^20 280.5 ms (0) -> 276.6 (1) / 276.9 (2); DRAM traffic
 // of the kernel 15.8 -> 6.3 GB per 2^16 pairings, local loads -25 %, local stores -16 %; with 3 blocks per SM (168
 // registers) 286.2 ms.  The spill traffic was not what bounds the kernel: the multiply pipe stays at 80 %.
+// State 3 (f + the Fp6 temporary of the in-place Fp12 operations, tower.cuh ZKP_INPLACE12): 273.7 ms, shipped.
 #ifndef ZKP_SMEM_STATE
-#define ZKP_SMEM_STATE 2
+#define ZKP_SMEM_STATE 3
+#endif
+#if ZKP_SMEM_STATE >= 3 && !ZKP_INPLACE12
+#error "ZKP_SMEM_STATE=3 keeps the in-place temporary in shared memory: needs ZKP_INPLACE12=1"
 #endif
 // (3 = f and the one Fp6 temporary of the in-place Fp12 operations, needs ZKP_INPLACE12; R thread-local)
 // bytes of shared memory per thread: 304 = 76 words (f + 16 pad), 432 = 108 words (f + R or f + T); both are 12 mod 32 words

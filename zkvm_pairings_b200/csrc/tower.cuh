@@ -21,6 +21,13 @@
 #pragma once
 #include "fp.cuh"
 
+// 1: the Miller loop squares f and multiplies it by a line IN PLACE with one Fp6 temporary (fp12_sqr_inplace,
+// fp12_mul_by_014_inplace below) instead of three thread-local ones per operation; 0: the out-of-place forms only.
+// Measured (profiles/r2d_miller_ab.txt): Miller loop at 2^20 276.4 -> 273.7 ms with f and the temporary in shared memory.
+#ifndef ZKP_INPLACE12
+#define ZKP_INPLACE12 1
+#endif
+
 namespace zkp {
 
 // ------------------------------------------------------------------ out-of-line Fp kernels
@@ -330,7 +337,7 @@ ZKP_NOINLINE void fp12_sqr(Fp12 &r, const Fp12 &a) {
     fp6_sub(t, t, ab);
     r.c0 = t;
 }
-#ifdef ZKP_INPLACE12
+#if ZKP_INPLACE12
 // In-place forms of the two Fp12 operations of the Miller loop: ONE Fp6 temporary (handed in by the caller, so that
 // it can live in shared memory next to f) instead of three thread-local ones each; same field elements.
 // (a0 + a1)(a0 + v a1) with the operand sums formed on the fly; r may alias a0 or a1
