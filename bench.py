@@ -220,8 +220,9 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL's own log (communicator / rank lines) stays on: it goes to stderr with everything else that
         # libraries print (main() parks the real stdout), so rank 0's stdout still carries ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"                   # never quieter than INFO: the communicator lines must be visible
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")  # (and no chattier than the init lines unless the caller asks)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -537,7 +538,7 @@ def bench_sliced(eng, z, sharding, torch, dist, world, rank, dev, st, total, see
     out = torch.empty((m, 72), dtype=torch.int64, device=dev)
     err = torch.zeros(1, dtype=torch.int32, device=dev)
     eng.gen_points_dev(seed, lo, m, g1, i1, g2, i2, stream=st)
-    eng.pairing_dev(z.MODE_PAIRING, out, g1=g1, g2=g2, n_checks=min(m, 4096), err=err, stream=st)    # warm-up
+    eng.pairing_dev(z.MODE_PAIRING, out, g1=g1, g2=g2, err=err, stream=st)    # full-size warm-up: grows the scratch pool (2.6 KB per pairing)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -279,7 +279,11 @@ struct CExp {            // one f^|x| between its two halves
     Fp2 t;               // d1 d2 d3: the Fp2 whose norm goes to the (batched) Fp inversion
 };
 // z = (z2, z3, z4, z5) <- the same four coefficients of the square; 6 Fp2 squarings
+#ifdef ZKP_CSQ_INLINE
+ZKP_HD void cyc_sqr_compressed(Fp2 *z) {
+#else
 ZKP_NOINLINE void cyc_sqr_compressed(Fp2 *z) {
+#endif
     Fp2 t0, t1, t2, t3;
     fp4_square(t0, t1, z[0], z[1]);
     ZKP_CODE_SYNC(6);
