@@ -136,7 +136,9 @@ int32_t zkp_miller_loop_batch(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t
                               const uint64_t *g2_xy, const uint8_t *g2_inf, size_t n, uint64_t *out_fp12);
 /* out_fp12[i] = in_fp12[i]^((p^12-1)/r) */
 int32_t zkp_final_exp_batch(zkp_ctx *ctx, const uint64_t *in_fp12, size_t n, uint64_t *out_fp12);
-/* out_gt[i] = e(G1[i], G2[i]) */
+/* out_gt[i] = e(G1[i], G2[i]).  Points must be curve points (zkp_g1_check_batch / zkp_g2_check_batch validate them): the
+ * fused path uses line steps that rely on the curve equation, so for off-curve inputs -- where no pairing is defined -- it need
+ * not agree with zkp_final_exp_batch(zkp_miller_loop_batch(.)), which applies SURVEY 9.1's formulas to whatever it is given. */
 int32_t zkp_pairing_batch(zkp_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_inf,
                           const uint64_t *g2_xy, const uint8_t *g2_inf, size_t n, uint64_t *out_gt);
 /* n_checks checks of pairs_per_check (<= ZKP_MAX_PAIRS_PER_CHECK) pairs each, stored check-major;
