@@ -279,6 +279,8 @@ struct CExp {            // one f^|x| between its two halves
     Fp2 t;               // d1 d2 d3: the Fp2 whose norm goes to the (batched) Fp inversion
 };
 // z = (z2, z3, z4, z5) <- the same four coefficients of the square; 6 Fp2 squarings
+// (ZKP_CSQ_INLINE / ZKP_CEXP_Z_SMEM: inlined into the loop / state in shared memory -- both measured neutral,
+// profiles/r2h_final_exp_variants.txt)
 #ifdef ZKP_CSQ_INLINE
 ZKP_HD void cyc_sqr_compressed(Fp2 *z) {
 #else
