@@ -381,7 +381,7 @@ ZKP_NOINLINE void cexp_end(Fp12 &r, const CExp &c, const Fp &ninv) {
 // SURVEY 9.2 as a pipeline of SIX stages separated by Fp inversions: the one of the easy part (f^-1,
 // fe_prepare leaves the cofactors and the norm) and one per f^x of the hard part (the decompression
 // above).  The GPU path runs every stage as a launch with a batched inversion kernel in between
-// (Montgomery's trick across pairings: ~41 Fp products per inverse instead of a 609-product Fermat ladder
+// (Montgomery's trick across pairings: 3 Fp products per inverse plus a 1/16 share of one binary-GCD inversion
 // per lane, pairing_kernel.cu); final_exponentiation() below chains the same stages with in-lane
 // inversions (dev simulation, small helpers).
 //
@@ -451,7 +451,7 @@ ZKP_HD void final_exponentiation(Fp12 &r, const Fp12 &f) {
 }
 
 // Montgomery's trick over a run of values held by ONE thread: v[i] <- 1/v[i] for i < cnt with a
-// single Fermat inversion and 3 (cnt - 1) products.  Zeros (a zero norm: only for a zero Fp12
+// single inversion (tower.cuh fp_inv) and 3 (cnt - 1) products.  Zeros (a zero norm: only for a zero Fp12
 // input, which maps to zero) are skipped and stay zero.  `pre` is scratch of cnt elements.
 ZKP_HD void fp_batch_inv(Fp *v, Fp *pre, int cnt) {
     Fp acc = fp_one();
@@ -470,7 +470,7 @@ ZKP_HD void fp_batch_inv(Fp *v, Fp *pre, int cnt) {
 
 // ------------------------------------------------------------------ group helpers (input prep)
 //
-// [k]P in Jacobian coordinates (a = 0 curves), k a 64-bit scalar, then one Fermat inversion back
+// [k]P in Jacobian coordinates (a = 0 curves), k a 64-bit scalar, then one inversion back
 // to affine.  Used to synthesise valid subgroup points on the device (k*G1gen, k*G2gen); the
 // reference's own random() points are off-curve (src/g1.rs:64-72) and its G1 scalar mul drops
 // bit 0 (src/g1.rs:130-153) -- this is the correct double-and-add of src/g2.rs:185-208.

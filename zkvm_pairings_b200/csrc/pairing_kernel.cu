@@ -34,19 +34,22 @@ cudaError_t zkp_launch_fe_stages(void *scratch, size_t n, uint64_t *out, uint8_t
 
 using namespace zkp;
 
-// ZKP_SMEM_STATE: 0 = all per-thread state in thread-local memory, 1 = f in shared memory, 2 = f and (K = 1) R.
-// Measured (profiles/r2b_smem_state_variants.txt): Miller loop at 2^20 280.5 ms (0) -> 276.6 (1) / 276.9 (2); DRAM traffic
-// of the kernel 15.8 -> 6.3 GB per 2^16 pairings, local loads -25 %, local stores -16 %; with 3 blocks per SM (168
-// registers) 286.2 ms.  The spill traffic was not what bounds the kernel: the multiply pipe stays at 80 %.
-// State 3 (f + the Fp6 temporary of the in-place Fp12 operations, tower.cuh ZKP_INPLACE12): 273.7 ms, shipped.
+// ZKP_SMEM_STATE -- which per-thread state lives in SHARED memory (a per-thread slice at a stride of 76 or 108 words,
+// both 12 mod 32, so that the 128-bit accesses of a quarter-warp fall into disjoint bank groups):
+//   0  nothing: f, R and every temporary in thread-local memory (round 1)
+//   1  the Miller accumulator f (304 B / thread)
+//   2  f and, for single pairings, the G2 accumulator R (432 B)
+//   3  f and the ONE Fp6 temporary of the in-place Fp12 operations (432 B; tower.cuh ZKP_INPLACE12) -- shipped
+// Measured, Miller loop at 2^20 (profiles/r2b_smem_state_variants.txt, r2d_miller_ab.txt, r2f_ncu_summary.txt):
+//   280.5 ms (0) -> 276.6 (1) / 276.9 (2) -> 273.7 (3); 3 blocks per SM at 168 registers 286.2, 5 blocks with state 1 300.2.
+//   DRAM traffic of the kernel per 2^16 pairings 15.76 GB (0) -> 6.26 (2) -> 0.92 (3); local loads 195.1M -> 146.5M -> 77.8M,
+//   local stores 100.1M -> 84.0M -> 42.4M; long-scoreboard stall 0.97 -> 0.86 -> 0.45 per issue; fmaheavy 79.9 -> 80.1 -> 82.2 %.
 #ifndef ZKP_SMEM_STATE
 #define ZKP_SMEM_STATE 3
 #endif
 #if ZKP_SMEM_STATE >= 3 && !ZKP_INPLACE12
 #error "ZKP_SMEM_STATE=3 keeps the in-place temporary in shared memory: needs ZKP_INPLACE12=1"
 #endif
-// (3 = f and the one Fp6 temporary of the in-place Fp12 operations, needs ZKP_INPLACE12; R thread-local)
-// bytes of shared memory per thread: 304 = 76 words (f + 16 pad), 432 = 108 words (f + R or f + T); both are 12 mod 32 words
 #define ZKP_SMEM_STRIDE(K) ((ZKP_SMEM_STATE >= 3 || ((K) == 1 && ZKP_SMEM_STATE == 2)) ? 432 : 304)
 
 // mode: bit0 Miller loop, bit1 first half of the final exponentiation.  One lane pair per check of
@@ -63,9 +66,7 @@ k_pairing(int mode, const uint64_t *__restrict__ g1, const uint8_t *__restrict__
     size_t e = i * (size_t)k, e2 = i * (size_t)(k - kf);   // the last kf pairs of a check use prepared G2 tables
     bool bad = false;
 #if ZKP_SMEM_STATE
-    // The Miller accumulator f (and, for single pairings, the G2 accumulator R) live in SHARED memory: a per-thread
-    // slice at a stride whose word count is 12 mod 32, so that the 128-bit accesses of a quarter-warp fall into
-    // disjoint bank groups (conflict-free) -- fixed ~30-cycle latency instead of thread-local frames that miss L1.
+    // this thread's slice of shared memory: f first, then R (state 2) or the in-place temporary (state 3)
     extern __shared__ uint4 zkp_smem[];
     char *slice = reinterpret_cast<char *>(zkp_smem) + (size_t)threadIdx.x * ZKP_SMEM_STRIDE(K);
     Fp12 &f = *reinterpret_cast<Fp12 *>(slice);
