@@ -168,6 +168,57 @@ void sim_batch_inv(const uint64_t *in, uint64_t *out, size_t n, int run) {
         for (int i = 0; i < cnt; i++) store_fp(out + 6 * (lo + i), v[i], nullptr);
     }
 }
+// Bound check of the Fp6-level bodies (in particular of their lazy-reduction forms, -DZKP_LAZY): every Montgomery
+// representative of an operand may lie anywhere in [0, 2p]; the recombined unreduced values are multilinear in them, so
+// their extremes are reached at the vertices of that box.  Runs fp6_mul (what = 0, 2^12 vertices), fp6_mul_by_01 (1, 2^10)
+// and fp4_square (2, 2^4) with every operand within 2^20 of 0 or of 2p and compares with the schoolbook formulas on
+// reduced Fp2 products; the ZKP_SIM_ASSERTs inside abort on a bound violation.  Returns the number of mismatches.
+static Fp vertex_fp(unsigned combo, int operand, int what) {
+    int bit = 2 * operand + lane_par();
+    uint32_t d = (uint32_t)(splitmix64_at(0xB0DD + what, (uint64_t)combo * 64 + bit) & 0xfffff);
+    Fp r = ((combo >> bit) & 1) ? fp_const(ZKP_2P) : fp_zero();
+    if ((combo >> bit) & 1) r.l[0] -= d;   // 2p - d (the low word of 2p is 0xffff5556: no borrow)
+    else r.l[0] = d;
+    return r;
+}
+static bool same_fp2(const Fp2 &x, const Fp2 &y) {
+    uint32_t a[ZKP_NL], b[ZKP_NL];
+    fp_to_words(a, x.c);
+    fp_to_words(b, y.c);
+    return lane_and(memcmp(a, b, sizeof a) == 0);
+}
+int sim_vertex_check(int what) {
+    std::atomic<int> bad{0};
+    const unsigned combos = what == 0 ? 1u << 12 : what == 1 ? 1u << 10 : 1u << 4;
+    run_pair([&]() {
+        for (unsigned c = 0; c < combos; c++) {
+            Fp2 v[6];
+            for (int k = 0; k < 6; k++) v[k].c = vertex_fp(c, k, what);
+            if (what == 0) {
+                Fp6 a = {v[0], v[1], v[2]}, b = {v[3], v[4], v[5]}, r;
+                fp6_mul(r, a, b);
+                Fp2 e0 = fp2_add(fp2_mul(a.c0, b.c0), fp2_mul_nr(fp2_add(fp2_mul(a.c1, b.c2), fp2_mul(a.c2, b.c1))));
+                Fp2 e1 = fp2_add(fp2_add(fp2_mul(a.c0, b.c1), fp2_mul(a.c1, b.c0)), fp2_mul_nr(fp2_mul(a.c2, b.c2)));
+                Fp2 e2 = fp2_add(fp2_add(fp2_mul(a.c0, b.c2), fp2_mul(a.c1, b.c1)), fp2_mul(a.c2, b.c0));
+                if (!(same_fp2(r.c0, e0) & same_fp2(r.c1, e1) & same_fp2(r.c2, e2))) bad++;
+            } else if (what == 1) {
+                Fp6 a = {v[0], v[1], v[2]}, r;
+                fp6_mul_by_01(r, a, v[3], v[4]);
+                Fp2 e0 = fp2_add(fp2_mul(a.c0, v[3]), fp2_mul_nr(fp2_mul(a.c2, v[4])));
+                Fp2 e1 = fp2_add(fp2_mul(a.c0, v[4]), fp2_mul(a.c1, v[3]));
+                Fp2 e2 = fp2_add(fp2_mul(a.c1, v[4]), fp2_mul(a.c2, v[3]));
+                if (!(same_fp2(r.c0, e0) & same_fp2(r.c1, e1) & same_fp2(r.c2, e2))) bad++;
+            } else {
+                Fp2 c0, c1;
+                fp4_square(c0, c1, v[0], v[1]);
+                Fp2 e0 = fp2_add(fp2_mul(v[0], v[0]), fp2_mul_nr(fp2_mul(v[1], v[1])));
+                Fp2 e1 = fp2_dbl(fp2_mul(v[0], v[1]));
+                if (!(same_fp2(c0, e0) & same_fp2(c1, e1))) bad++;
+            }
+        }
+    });
+    return bad.load();
+}
 // wide MACs executed by both lanes since the last call (boundary conversions included)
 uint64_t sim_take_mac_count() { return g_macs.exchange(0); }
 uint64_t sim_splitmix64_at(uint64_t seed, uint64_t idx) { return splitmix64_at(seed, idx); }

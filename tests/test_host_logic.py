@@ -317,6 +317,57 @@ def test_sim_batch_inversion(sim, coracle, pyref):
     assert util.arr_fp(out)[0] == 0 and util.arr_fp(out)[16] == 1
 
 
+def _sim_variant(defs):
+    """the dev simulation built with extra -D flags (a build variant of the device headers)"""
+    d = os.path.join(ROOT, "tests", "host_sim")
+    so = os.path.join(d, "libzkpair_sim_%s.so" % re.sub(r"\W+", "_", "".join(defs)))
+    src = [os.path.join(d, "sim.cpp")] + [os.path.join(ROOT, "zkvm_pairings_b200", "csrc", f)
+                                          for f in ("fp.cuh", "tower.cuh", "pairing.cuh", "ops.cuh", "consts.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared"] + list(defs) + ["-o", so, src[0]])
+    return ctypes.CDLL(so)
+
+
+def test_sim_fp6_bodies_at_the_vertices_of_the_operand_box(sim):
+    """fp6_mul / fp6_mul_by_01 / fp4_square with every operand representative next to 0 or next to 2p (all 2^12 / 2^10 /
+    2^4 combinations) against the schoolbook formulas: the operand-bound asserts inside must hold at the extremes."""
+    for what in (0, 1, 2):
+        assert sim.sim_vertex_check(what) == 0
+
+
+def test_sim_lazy_reduction_variant(coracle, pyref):
+    """The lazy-reduction build variant (-DZKP_LAZY=7, tower.cuh: unreduced Fp2 products recombined as 768-bit integers,
+    3 / 3 / 2 reductions per Fp6 product / sparse product / Fp4 square) computes the same field elements: worst-case
+    operand vertices (where its bounds are tight), tower ops, golden pairing vectors, and the work it saves."""
+    lazy = _sim_variant(["-DZKP_LAZY=7"])
+    for what in (0, 1, 2):
+        assert lazy.sim_vertex_check(what) == 0
+    from zkvm_pairings_b200 import TOWER_OPS, op_widths
+    for name in ("fp6_mul", "fp6_mul_by_01", "fp6_sqr", "fp12_mul", "fp12_sqr", "fp12_mul_by_014", "fp12_inv", "fp12_cyclotomic_sqr"):
+        if name not in TOWER_OPS:
+            continue
+        code = TOWER_OPS[name]
+        na, nb, nr = op_widths(name)
+        n = 10
+        a = util.random_fp_matrix(n, na, seed=code + 7)
+        b = util.random_fp_matrix(n, nb, seed=code + 107) if nb else None
+        out, st = np.zeros((n, 6 * nr), np.uint64), np.zeros(n, np.uint8)
+        lazy.sim_tower_op(code, _p(a), _p(b), _p(out), _p(st), ctypes.c_size_t(n))
+        assert np.array_equal(out, coracle.tower_op(name, a, b)), name
+    g1, i1, g2, i2 = util.oracle_points(coracle, 0x5EED, 0, 3)
+    ml, gt = np.zeros((3, 72), np.uint64), np.zeros((3, 72), np.uint64)
+    assert lazy.sim_pairing(1, _p(g1), _p(i1), _p(g2), _p(i2), ctypes.c_size_t(3), 1, None, _p(ml), None) == 0
+    assert lazy.sim_pairing(3, _p(g1), _p(i1), _p(g2), _p(i2), ctypes.c_size_t(3), 1, None, _p(gt), None) == 0
+    assert np.array_equal(ml, coracle.miller_loop_batch(g1, i1, g2, i2)) and np.array_equal(gt, coracle.pairing_batch(g1, i1, g2, i2))
+    lazy.sim_take_mac_count.restype = ctypes.c_uint64
+    lazy.sim_take_mac_count()
+    lazy.sim_pairing(1, _p(g1), None, _p(g2), None, ctypes.c_size_t(1), 1, None, _p(ml), None)
+    miller = lazy.sim_take_mac_count()
+    lazy.sim_pairing(2, None, None, None, None, ctypes.c_size_t(1), 1, _p(ml), _p(gt), None)
+    fexp = lazy.sim_take_mac_count()
+    assert (miller, fexp) == (1841352, 1534416)   # reduced forms: 2041032 / 1829256 (test_sim_executed_mac_count)
+
+
 def test_sim_executed_mac_count(sim, coracle):
     """Work accounting behind bench.py's `executed_macs_per_pairing`: the dev simulation counts the
     32x32->64 MACs both lanes issue (300 per Montgomery product, 444 per two-product form)."""

@@ -393,6 +393,159 @@ ZKP_HD Fp mont_mul2(const Fp &u, const Fp &v, const Fp &w, const Fp &z) {
 // Value-equivalent (after conversion) to src/fp.rs:413-434 / :452-455.
 ZKP_HD Fp fp_mul(const Fp &a, const Fp &b) { return mont_mul(a, b); }
 
+// ------------------------------------------------------------------ unreduced ("wide") values: lazy reduction
+//
+// A Montgomery reduction is 156 of the 300 wide MACs of a product.  Where several products are only ever added to or
+// subtracted from each other before anybody looks at them (the Karatsuba recombination of an Fp6 product, an Fp4
+// square), the products are kept UNREDUCED -- 24 words, at most 8 p^2 each for 2p-redundant operands -- recombined by
+// plain 768-bit additions and subtractions modulo 2^768 (no correction steps), and only the results are reduced:
+// 3 reductions instead of 6 per lane for an Fp6 product (tower.cuh).  Intermediate values may wrap around modulo
+// 2^768; before the reduction a constant multiple of p^2 (ZKP_P2X8 etc., = 0 mod p) is added that makes the TRUE value
+// non-negative, and the call sites keep it below 2^768 = 96.9 p^2 (bounds stated at each call site, interval
+// arithmetic over the operand bound 2p).
+struct alignas(16) FpW {
+    uint32_t l[2 * ZKP_NL];
+};
+// One row of a plain product, E/O += a * b * 2^(32 i), on split accumulators like the CIOS rows above: E holds the
+// 64-bit columns at even words (E[k] = word k), O the columns at odd words (O[k] = word k + 1).  The carry out of
+// a chain lands in a word no earlier row has used for data (it holds at most the carries of the neighbouring rows).
+ZKP_HD void wide_row(uint32_t *E, uint32_t *O, const uint32_t *a, uint32_t b, int i) {
+    // The chain over the odd limbs ends with a[11] * b < 2^63 (a <= 4p: a[11] <= 0x68044800) on top of a column that
+    // so far holds only a few carries: no carry out.  The chain over the even limbs ends with a[10] * b: its carry is
+    // absorbed by the next word up, which is either untouched or holds the carries of the neighbouring rows.
+    if ((i & 1) == 0) {
+        chain_mad<1>(O + i, a, b);
+        chain_mad<0>(E + i, a, b);
+        E[i + ZKP_NL] = addc(E[i + ZKP_NL], 0);
+    } else {
+        chain_mad<1>(E + i + 1, a, b);
+        chain_mad<0>(O + i - 1, a, b);
+        O[i + ZKP_NL - 1] = addc(O[i + ZKP_NL - 1], 0);
+    }
+}
+ZKP_HD FpW wide_merge(const uint32_t *E, const uint32_t *O) {
+    FpW t;
+    t.l[0] = E[0];
+    t.l[1] = add_cc(E[1], O[0]);
+#pragma unroll
+    for (int k = 2; k < 2 * ZKP_NL - 1; k++) t.l[k] = addc_cc(E[k], O[k - 1]);
+    t.l[2 * ZKP_NL - 1] = addc(E[2 * ZKP_NL - 1], O[2 * ZKP_NL - 2]);
+    return t;
+}
+// u * v + w * z, unreduced: 288 wide MACs.  Operands <= 2p each (u, w may be <= 4p): <= 16 p^2.
+ZKP_HD FpW mul_wide2(const Fp &u, const Fp &v, const Fp &w, const Fp &z) {
+#ifndef ZKP_DEVICE_BUILD
+    zkp_sim_macs += 288;
+    ZKP_SIM_ASSERT(fp_leq_4p(u) && fp_leq_2p(v) && fp_leq_4p(w) && fp_leq_2p(z), "mul_wide2 operand bound");
+#endif
+    uint32_t E[2 * ZKP_NL], O[2 * ZKP_NL];
+#pragma unroll
+    for (int k = 0; k < 2 * ZKP_NL; k++) E[k] = O[k] = 0;
+#pragma unroll
+    for (int i = 0; i < ZKP_NL; i++) {
+        wide_row(E, O, u.l, v.l[i], i);
+        wide_row(E, O, w.l, z.l[i], i);
+    }
+    return wide_merge(E, O);
+}
+// u * v, unreduced: 144 wide MACs.  u <= 4p, v <= 2p.
+ZKP_HD FpW mul_wide(const Fp &u, const Fp &v) {
+#ifndef ZKP_DEVICE_BUILD
+    zkp_sim_macs += 144;
+    ZKP_SIM_ASSERT(fp_leq_4p(u) && fp_leq_2p(v), "mul_wide operand bound");
+#endif
+    uint32_t E[2 * ZKP_NL], O[2 * ZKP_NL];
+#pragma unroll
+    for (int k = 0; k < 2 * ZKP_NL; k++) E[k] = O[k] = 0;
+#pragma unroll
+    for (int i = 0; i < ZKP_NL; i++) wide_row(E, O, u.l, v.l[i], i);
+    return wide_merge(E, O);
+}
+// 768-bit arithmetic modulo 2^768 (wrap-around is harmless as long as the value that is finally reduced is in range)
+ZKP_HD FpW fpw_add(const FpW &a, const FpW &b) {
+    FpW r;
+    r.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 2 * ZKP_NL - 1; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+    r.l[2 * ZKP_NL - 1] = addc(a.l[2 * ZKP_NL - 1], b.l[2 * ZKP_NL - 1]);
+    return r;
+}
+ZKP_HD FpW fpw_sub(const FpW &a, const FpW &b) {
+    FpW r;
+    r.l[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 2 * ZKP_NL - 1; i++) r.l[i] = subc_cc(a.l[i], b.l[i]);
+    r.l[2 * ZKP_NL - 1] = subc(a.l[2 * ZKP_NL - 1], b.l[2 * ZKP_NL - 1]);
+    return r;
+}
+ZKP_HD FpW fpw_add_const(const FpW &a, const uint32_t *k) {   // k = 24 constant words
+    FpW r;
+    r.l[0] = add_cc(a.l[0], k[0]);
+#pragma unroll
+    for (int i = 1; i < 2 * ZKP_NL - 1; i++) r.l[i] = addc_cc(a.l[i], k[i]);
+    r.l[2 * ZKP_NL - 1] = addc(a.l[2 * ZKP_NL - 1], k[2 * ZKP_NL - 1]);
+    return r;
+}
+ZKP_HD FpW fpw_xchg(const FpW &a) {
+#ifdef ZKP_DEVICE_BUILD
+    FpW r;
+#pragma unroll
+    for (int i = 0; i < 2 * ZKP_NL; i++) r.l[i] = word_xchg(a.l[i]);
+    return r;
+#else
+    FpW r = a;
+    zkp_sim_xchg(&r, sizeof(FpW));
+    return r;
+#endif
+}
+// One row of a reduction WITHOUT a product row in front of it: x enters the even role, y the odd role (and moves
+// down 64 bits inside its chain, exactly as in row_next); m clears the low word.
+ZKP_HD void row_shift_reduce(uint32_t *x, uint32_t *y) {
+    x[0] = add_cc(x[0], y[1]);
+    uint32_t m = x[0] * ZKP_N0INV;
+    chain_mad_rshift(y, ZKP_P, m);
+    chain_mad<0>(x, ZKP_P, m);
+    y[ZKP_NL - 1] = addc(y[ZKP_NL - 1], 0);
+}
+// T / 2^384 mod p for an unreduced T < 2^768: 156 wide MACs.  T = Tlo + Thi 2^384: the low half is reduced
+// ((Tlo + m p) / 2^384 <= p), the high half added on top: result < T / 2^384 + p + 1 -- the CALLER corrects
+// it back to [0, 2p] according to its bound on T (fp_correct / fp_correct8).
+ZKP_HD Fp mont_redc(const FpW &t) {
+#ifndef ZKP_DEVICE_BUILD
+    zkp_sim_macs += 156;
+#endif
+    uint32_t ev[ZKP_NL], od[ZKP_NL];
+#pragma unroll
+    for (int i = 0; i < ZKP_NL; i++) {
+        ev[i] = t.l[i];
+        od[i] = 0;
+    }
+    row_reduce(ev, od);
+#pragma unroll
+    for (int i = 1; i < ZKP_NL; i += 2) {
+        row_shift_reduce(od, ev);
+        if (i + 1 < ZKP_NL) row_shift_reduce(ev, od);
+    }
+    Fp r = mont_finish(ev, od);
+    r.l[0] = add_cc(r.l[0], t.l[ZKP_NL]);
+#pragma unroll
+    for (int i = 1; i < ZKP_NL - 1; i++) r.l[i] = addc_cc(r.l[i], t.l[ZKP_NL + i]);
+    r.l[ZKP_NL - 1] = addc(r.l[ZKP_NL - 1], t.l[2 * ZKP_NL - 1]);
+    return r;
+}
+// a in [0, 8p) -> [0, 2p]: subtract 4p, then 2p, each when that does not go negative
+ZKP_HD Fp fp_correct8(const Fp &s) {
+    Fp t;
+    t.l[0] = sub_cc(s.l[0], ZKP_4P[0]);
+#pragma unroll
+    for (int i = 1; i < ZKP_NL; i++) t.l[i] = subc_cc(s.l[i], ZKP_4P[i]);
+    bool neg = subc(0, 0) != 0;
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < ZKP_NL; i++) r.l[i] = neg ? s.l[i] : t.l[i];
+    return fp_correct(r);
+}
+
 // ------------------------------------------------------------------ boundary conversions
 //
 // Canonical form = 12 saturated 32-bit words (= the six u64 limbs of src/fp.rs:24), value in [0,p).

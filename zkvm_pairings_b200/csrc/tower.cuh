@@ -28,10 +28,23 @@
 #define ZKP_INPLACE12 1
 #endif
 
+// Multiply-pipe token (pairing_kernel.cu, tools/ring_probe.cu): the MAC-dense bodies below are bracketed by these two
+// hooks; a kernel may define them so that the warps sharing a scheduler enter the bodies one after the other (FIFO)
+// instead of time-slicing the multiply pipe.  Default: nothing.
+#ifndef ZKP_PIPE_ACQUIRE
+#define ZKP_PIPE_ACQUIRE() do { } while (0)
+#define ZKP_PIPE_RELEASE() do { } while (0)
+#endif
+
 namespace zkp {
 
 // ------------------------------------------------------------------ out-of-line Fp kernels
-ZKP_NOINLINE Fp fmul(Fp a, Fp b) { return fp_mul(a, b); }
+ZKP_NOINLINE Fp fmul(Fp a, Fp b) {
+    ZKP_PIPE_ACQUIRE();
+    Fp r = fp_mul(a, b);
+    ZKP_PIPE_RELEASE();
+    return r;
+}
 #define fsqr(a) fmul((a), (a))
 
 // 1/a mod p (the value of Fp::invert, src/fp.rs:306-319, which walks the exponent p - 2, src/fp.rs:264-276; zero maps
@@ -181,7 +194,9 @@ ZKP_NOINLINE Fp2 fp2_mul(Fp2 a, Fp2 b) {
     Fp t = fp_xchg(fp_select(odd, fp_neg(a.c), a.c));
     Fp b0 = fp_bcast<0>(b.c), b1 = fp_bcast<1>(b.c);
     Fp2 r;
+    ZKP_PIPE_ACQUIRE();
     r.c = mont_mul2(a.c, b0, t, b1);
+    ZKP_PIPE_RELEASE();
     return r;
 }
 // Square (complex method, src/fp2.rs:171-189): even lane (a0+a1)(a0-a1), odd lane (2 a0) a1.
@@ -194,9 +209,70 @@ ZKP_NOINLINE Fp2 fp2_sqr(Fp2 a) {
     Fp x = fp_add_lazy(fp_bcast<0>(a.c), pa);
     Fp y = fp_select(odd, a.c, fp_sub(a.c, pa));
     Fp2 r;
+    ZKP_PIPE_ACQUIRE();
     r.c = mont_mul(x, y);
+    ZKP_PIPE_RELEASE();
     return r;
 }
+// ---- unreduced Fp2 products (fp.cuh FpW): this lane's component, at most 8 p^2, to be recombined and reduced later
+// ZKP_LAZY -- lazy reduction (fp.cuh FpW): bit 0 Fp6 products, bit 1 fp6_mul_by_01, bit 2 Fp4 squares recombine UNREDUCED
+// Fp2 products (3 / 3 / 2 reductions instead of 6 / 5 / 3 per lane: Miller loop -9.8 %, final exponentiation -16.1 % wide
+// MACs, bit-identical results, GPU suite green).  Measured at 2^20 (profiles/r2l_lazy_reduction.txt): the 768-bit
+// recombinations, their spills and the larger code give back what the multiplier saves -- Miller loop 273.3 -> 269.7..271.7
+// ms, final exponentiation 260.5 -> 262.4..266.7 ms, pairing 521.5..523.3 -> 517.3..519.9 ms (-0.6 %) -- so the shipped
+// build keeps the reduced forms (0); the lazy forms stay as a tested build variant.
+#ifndef ZKP_LAZY
+#define ZKP_LAZY 0
+#endif
+ZKP_NOINLINE FpW fp2_mulw(Fp2 a, Fp2 b) {
+    ZKP_CODE_SYNC(5);
+    bool odd = lane_par() != 0;
+    Fp t = fp_xchg(fp_select(odd, fp_neg(a.c), a.c));
+    Fp b0 = fp_bcast<0>(b.c), b1 = fp_bcast<1>(b.c);
+    ZKP_PIPE_ACQUIRE();
+    FpW r = mul_wide2(a.c, b0, t, b1);
+    ZKP_PIPE_RELEASE();
+    return r;
+}
+ZKP_NOINLINE FpW fp2_sqrw(Fp2 a) {
+    ZKP_CODE_SYNC(5);
+    bool odd = lane_par() != 0;
+    Fp pa = fp_xchg(a.c);
+    Fp x = fp_add_lazy(fp_bcast<0>(a.c), pa);
+    Fp y = fp_select(odd, a.c, fp_sub(a.c, pa));
+    ZKP_PIPE_ACQUIRE();
+    FpW r = mul_wide(x, y);
+    ZKP_PIPE_RELEASE();
+    return r;
+}
+// xi * X for an unreduced Fp2 value (X = this lane's component, Y = the partner's): X - Y in the even lane,
+// X + Y in the odd lane, modulo 2^768; the subtraction is the two's complement (~Y + 1) so that both lanes run the
+// same carry chain
+ZKP_HD FpW fpw_mul_nr(const FpW &x) {
+    FpW y = fpw_xchg(x);
+    const uint32_t m = lane_par() != 0 ? 0u : 0xffffffffu;
+    FpW r;
+    add_cc(m, 1u);   // carry flag <- 1 in the even lane
+#pragma unroll
+    for (int i = 0; i < 2 * ZKP_NL - 1; i++) r.l[i] = addc_cc(x.l[i], y.l[i] ^ m);
+    r.l[2 * ZKP_NL - 1] = addc(x.l[2 * ZKP_NL - 1], y.l[2 * ZKP_NL - 1] ^ m);
+    return r;
+}
+// reduce a recombined value (the caller has added the multiple of p^2 that makes it non-negative).
+// BIG = 0: value < 29 p^2 (result < 4p, one correction); 1: < 68 p^2 (result < 8p, two corrections)
+template <int BIG>
+ZKP_NOINLINE Fp2 fp2_redc(FpW t) {
+    ZKP_PIPE_ACQUIRE();
+    Fp r = mont_redc(t);
+    ZKP_PIPE_RELEASE();
+#ifndef ZKP_DEVICE_BUILD
+    ZKP_SIM_ASSERT(BIG ? !fp_geq_const(r, ZKP_8P) : fp_leq_4p(r), "fp2_redc result bound");
+#endif
+    Fp2 o;
+    o.c = BIG ? fp_correct8(r) : fp_correct(r);
+    return o;
+}
+
 ZKP_HD Fp2 fp2_mul_fp(const Fp2 &a, const Fp &k) { Fp2 r; r.c = fmul(a.c, k); return r; }   // src/fp2.rs:95-102
 // src/fp2.rs:278-296 ; zero maps to zero.  Split around the Fp inversion of the norm so that the
 // pairing kernels can batch that inversion over many pairings (pairing_kernel.cu):
@@ -230,6 +306,31 @@ ZKP_HD void fp6_mul_nr(Fp6 &r, const Fp6 &a) {
     r.c0 = t;
 }
 // Karatsuba, 6 Fp2 mul (value-equal to mul_interleaved, src/fp6.rs:188-267); r may alias a or b
+#if ZKP_LAZY & 1
+// Lazy reduction: the six products stay unreduced (v, w <= 8 p^2 per lane) and are recombined as 768-bit integers;
+// three reductions per lane instead of six (2196 wide MACs instead of 2664).  Bounds in units of p^2, true values:
+//   c0 = v0 - xi (v1 + v2 - w0):  inner in [-8, 16]; xi: even lane [-24, 24], odd [-16, 32];  c0 in [-32, 32]  -> + 32: [0, 64]
+//   c1 = w1 + xi v2 - v0 - v1:    xi v2: even [-8, 8], odd [0, 16];                           c1 in [-24, 24]  -> + 24: [0, 48]
+//   c2 = w2 + v1 - v0 - v2:                                                                   c2 in [-16, 16]  -> + 16: [0, 32]
+// all below 2^768 = 96.9 p^2 and below 68 p^2 (results < 8p: two correction steps).
+ZKP_NOINLINE void fp6_mul(Fp6 &r, const Fp6 &a, const Fp6 &b) {
+    ZKP_CODE_SYNC(4);
+    FpW v1 = fp2_mulw(a.c1, b.c1);
+    FpW v2 = fp2_mulw(a.c2, b.c2);
+    FpW w = fp2_mulw(fp2_add(a.c1, a.c2), fp2_add(b.c1, b.c2));
+    FpW t0 = fpw_mul_nr(fpw_sub(fpw_add(v1, v2), w));
+    FpW v0 = fp2_mulw(a.c0, b.c0);
+    Fp2 c0 = fp2_redc<1>(fpw_add_const(fpw_sub(v0, t0), ZKP_P2X32));
+    w = fp2_mulw(fp2_add(a.c0, a.c1), fp2_add(b.c0, b.c1));
+    FpW t1 = fpw_sub(fpw_add(w, fpw_mul_nr(v2)), fpw_add(v0, v1));
+    Fp2 c1 = fp2_redc<1>(fpw_add_const(t1, ZKP_P2X24));
+    w = fp2_mulw(fp2_add(a.c0, a.c2), fp2_add(b.c0, b.c2));
+    FpW t2 = fpw_sub(fpw_add(w, v1), fpw_add(v0, v2));
+    r.c2 = fp2_redc<1>(fpw_add_const(t2, ZKP_P2X16));
+    r.c0 = c0;
+    r.c1 = c1;
+}
+#else
 ZKP_NOINLINE void fp6_mul(Fp6 &r, const Fp6 &a, const Fp6 &b) {
     ZKP_CODE_SYNC(4);
     Fp2 v0 = fp2_mul(a.c0, b.c0);
@@ -242,6 +343,7 @@ ZKP_NOINLINE void fp6_mul(Fp6 &r, const Fp6 &a, const Fp6 &b) {
     r.c1 = fp2_add(t1, fp2_mul_nr(v2));
     r.c2 = fp2_add(t2, v1);
 }
+#endif
 // src/fp6.rs:274-288 ; r may alias a
 ZKP_NOINLINE void fp6_sqr(Fp6 &r, const Fp6 &a) {
     ZKP_CODE_SYNC(4);
@@ -265,6 +367,25 @@ ZKP_NOINLINE void fp6_mul_by_1(Fp6 &r, const Fp6 &a, const Fp2 &c1) {
     r.c0 = t0; r.c1 = t1; r.c2 = t2;
 }
 // a * (c0, c1, 0)  -- src/fp6.rs:110-125 ; r may alias a
+#if ZKP_LAZY & 2
+// Lazy reduction: 5 unreduced products, 3 reductions (1908 wide MACs per lane instead of 2220).  xi (a2 c1) is formed as
+// a2 (xi c1), so no unreduced value crosses the lane pair.  Bounds (units of p^2, true values):
+//   r0 = a0 c0 + a2 (xi c1) in [0, 16];  r1 = (c0 + c1)(a0 + a1) - a0 c0 - a1 c1 in [-16, 8] -> + 16: [0, 24];
+//   r2 = a2 c0 + a1 c1 in [0, 16]: all below 29 p^2 (results < 4p, one correction step)
+ZKP_NOINLINE void fp6_mul_by_01(Fp6 &r, const Fp6 &a, const Fp2 &c0, const Fp2 &c1) {
+    ZKP_CODE_SYNC(4);
+    FpW aa = fp2_mulw(a.c0, c0);
+    FpW t = fp2_mulw(a.c2, fp2_mul_nr(c1));
+    Fp2 r0 = fp2_redc<0>(fpw_add(aa, t));
+    FpW bb = fp2_mulw(a.c1, c1);
+    t = fp2_mulw(fp2_add(c0, c1), fp2_add(a.c0, a.c1));
+    Fp2 r1 = fp2_redc<0>(fpw_add_const(fpw_sub(t, fpw_add(aa, bb)), ZKP_P2X16));
+    t = fp2_mulw(a.c2, c0);
+    r.c2 = fp2_redc<0>(fpw_add(t, bb));
+    r.c0 = r0;
+    r.c1 = r1;
+}
+#else
 ZKP_NOINLINE void fp6_mul_by_01(Fp6 &r, const Fp6 &a, const Fp2 &c0, const Fp2 &c1) {
     ZKP_CODE_SYNC(4);
     Fp2 a_a = fp2_mul(a.c0, c0);
@@ -274,6 +395,7 @@ ZKP_NOINLINE void fp6_mul_by_01(Fp6 &r, const Fp6 &a, const Fp2 &c0, const Fp2 &
     Fp2 t3 = fp2_add(fp2_mul(a.c2, c0), b_b);
     r.c0 = t1; r.c1 = t2; r.c2 = t3;
 }
+#endif
 // src/fp6.rs:291-309 ; zero maps to zero ; r may alias a.  Split like fp2_inv: `c` receives the three
 // cofactors, the return value is the Fp2 whose inverse scales them.
 ZKP_NOINLINE Fp2 fp6_inv_prepare(Fp6 &c, const Fp6 &a) {
@@ -340,7 +462,24 @@ ZKP_NOINLINE void fp12_sqr(Fp12 &r, const Fp12 &a) {
 #if ZKP_INPLACE12
 // In-place forms of the two Fp12 operations of the Miller loop: ONE Fp6 temporary (handed in by the caller, so that
 // it can live in shared memory next to f) instead of three thread-local ones each; same field elements.
-// (a0 + a1)(a0 + v a1) with the operand sums formed on the fly; r may alias a0 or a1
+// (a0 + a1)(a0 + v a1); r may alias a0 (not a1)
+// ZKP_SUMS_SIMPLE = 1 (shipped): the second operand sum goes to a thread-local Fp6 and fp6_mul does the rest -- 26 KB less
+// hot code, 21 Fp2 additions and 4 xi-multiplications fewer per Fp12 squaring than forming every sum on the fly (0):
+// Miller loop at 2^20 273.3 -> 272.0 ms (profiles/r2l_lazy_reduction.txt)
+#ifndef ZKP_SUMS_SIMPLE
+#define ZKP_SUMS_SIMPLE 1
+#endif
+#if (ZKP_LAZY & 1) || ZKP_SUMS_SIMPLE
+ZKP_NOINLINE void fp6_mul_sums(Fp6 &r, const Fp6 &a0, const Fp6 &a1) {
+    Fp6 b;
+    b.c0 = fp2_add(a0.c0, fp2_mul_nr(a1.c2));
+    b.c1 = fp2_add(a0.c1, a1.c0);
+    b.c2 = fp2_add(a0.c2, a1.c1);
+    fp6_add(r, a0, a1);
+    fp6_mul(r, r, b);
+}
+#else
+// ... with the operand sums formed on the fly; r may alias a0 or a1
 ZKP_NOINLINE void fp6_mul_sums(Fp6 &r, const Fp6 &a0, const Fp6 &a1) {
     ZKP_CODE_SYNC(4);
     Fp2 v0 = fp2_mul(fp2_add(a0.c0, a1.c0), fp2_add(a0.c0, fp2_mul_nr(a1.c2)));
@@ -366,6 +505,7 @@ ZKP_NOINLINE void fp6_mul_sums(Fp6 &r, const Fp6 &a0, const Fp6 &a1) {
     r.c1 = fp2_add(t1, fp2_mul_nr(v2));
     r.c2 = fp2_add(t2, v1);
 }
+#endif
 // f <- f^2 (complex squaring, src/fp12.rs:173-184): T = c0 c1; c0 <- (c0 + c1)(c0 + v c1) - T - v T; c1 <- 2 T
 ZKP_NOINLINE void fp12_sqr_inplace(Fp12 &f, Fp6 &T) {
     fp6_mul(T, f.c0, f.c1);
@@ -460,12 +600,25 @@ ZKP_NOINLINE void fp12_frobenius(Fp12 &r, const Fp12 &a, int k) {
 }
 
 // Granger-Scott squaring in the cyclotomic subgroup: 9 Fp2 squarings.  r may alias f.
+#if ZKP_LAZY & 4
+// Lazy reduction: 3 unreduced squares (<= 8 p^2 per lane), 2 reductions (744 wide MACs per lane instead of 900).
+//   c0 = a^2 + xi b^2:  xi b^2 even lane [-8, 8], odd [0, 16];  c0 in [-8, 24] -> + 8: [0, 32]  (< 68 p^2: two corrections)
+//   c1 = (a + b)^2 - a^2 - b^2 in [-16, 8] -> + 16: [0, 24]                                     (< 29 p^2: one correction)
+// c0, c1 must not alias a, b.
+ZKP_HD void fp4_square(Fp2 &c0, Fp2 &c1, const Fp2 &a, const Fp2 &b) {
+    FpW pa = fp2_sqrw(a), pb = fp2_sqrw(b);
+    c0 = fp2_redc<1>(fpw_add_const(fpw_add(pa, fpw_mul_nr(pb)), ZKP_P2X8));
+    FpW ps = fp2_sqrw(fp2_add(a, b));
+    c1 = fp2_redc<0>(fpw_add_const(fpw_sub(ps, fpw_add(pa, pb)), ZKP_P2X16));
+}
+#else
 ZKP_HD void fp4_square(Fp2 &c0, Fp2 &c1, const Fp2 &a, const Fp2 &b) {
     Fp2 t0 = fp2_sqr(a);
     Fp2 t1 = fp2_sqr(b);
     c0 = fp2_add(fp2_mul_nr(t1), t0);
     c1 = fp2_sub(fp2_sub(fp2_sqr(fp2_add(a, b)), t0), t1);
 }
+#endif
 // 3t - 2z = 2(t - z) + t  and  3t + 2z = 2(t + z) + t
 ZKP_HD Fp2 cyc_minus(const Fp2 &t, const Fp2 &z) {
     Fp2 w = fp2_sub(t, z);
