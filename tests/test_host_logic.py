@@ -366,6 +366,16 @@ def test_sim_lazy_reduction_variant(coracle, pyref):
     lazy.sim_pairing(2, None, None, None, None, ctypes.c_size_t(1), 1, _p(ml), _p(gt), None)
     fexp = lazy.sim_take_mac_count()
     assert (miller, fexp) == (1841352, 1534416)   # reduced forms: 2041032 / 1829256 (test_sim_executed_mac_count)
+    # the SHIPPED combination (pairing_kernel.cu ZKP_MILLER_LAZY = 3: lazy Fp6 products and line products in the Miller unit,
+    # reduced forms in the final-exponentiation unit) executes 1841352 + 1829256 wide MACs per pairing in this accounting
+    lazy3 = _sim_variant(["-DZKP_LAZY=3"])
+    lazy3.sim_take_mac_count.restype = ctypes.c_uint64
+    lazy3.sim_take_mac_count()
+    ml3 = np.zeros((3, 72), np.uint64)
+    assert lazy3.sim_pairing(1, _p(g1), _p(i1), _p(g2), _p(i2), ctypes.c_size_t(3), 1, None, _p(ml3), None) == 0
+    assert lazy3.sim_take_mac_count() == 3 * 1841352 and np.array_equal(ml3, coracle.miller_loop_batch(g1, i1, g2, i2))
+    src = open(os.path.join(ROOT, "zkvm_pairings_b200", "csrc", "pairing_kernel.cu")).read()
+    assert re.search(r"#define ZKP_MILLER_LAZY 3\b", src) and "#define ZKP_LAZY ZKP_MILLER_LAZY" in src
 
 
 def test_sim_executed_mac_count(sim, coracle):

@@ -18,6 +18,18 @@
 #define ZKP_MILLER_SYNC 4
 #endif
 #define ZKP_LOOP_SYNC ZKP_MILLER_SYNC
+// Lazy reduction (tower.cuh ZKP_LAZY, fp.cuh FpW) in THIS unit only: ZKP_MILLER_LAZY = 3 (shipped) recombines UNREDUCED Fp2
+// products in the Fp6 products and the sparse line products of the Miller loop -- 3 reductions instead of 6 / 5 per lane,
+// -9.8 % wide MACs per Miller loop, bit-identical results.  Measured at 2^20, three interleaved repetitions
+// (profiles/r2l_lazy_reduction.txt, call r2t): pairing 520.5 -> 516.4 ms (-0.8 %), 2^16 pairings 34.8 -> 34.4 ms, 4-pair checks
+// 265.2..268.0 -> 264.2 ms, with prepared tables 220.1..221.8 -> 214.8 ms (-2.7 %).  The final-exponentiation unit keeps the
+// reduced forms (the lazy Fp4 squares measured +2 % there: larger hot loop, more spills).
+#ifndef ZKP_MILLER_LAZY
+#define ZKP_MILLER_LAZY 3
+#endif
+#ifndef ZKP_LAZY
+#define ZKP_LAZY ZKP_MILLER_LAZY
+#endif
 #include "../../include/zkpair.h"
 #include "fe_scratch.cuh"
 

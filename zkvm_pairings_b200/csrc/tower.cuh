@@ -217,10 +217,10 @@ ZKP_NOINLINE Fp2 fp2_sqr(Fp2 a) {
 // ---- unreduced Fp2 products (fp.cuh FpW): this lane's component, at most 8 p^2, to be recombined and reduced later
 // ZKP_LAZY -- lazy reduction (fp.cuh FpW): bit 0 Fp6 products, bit 1 fp6_mul_by_01, bit 2 Fp4 squares recombine UNREDUCED
 // Fp2 products (3 / 3 / 2 reductions instead of 6 / 5 / 3 per lane: Miller loop -9.8 %, final exponentiation -16.1 % wide
-// MACs, bit-identical results, GPU suite green).  Measured at 2^20 (profiles/r2l_lazy_reduction.txt): the 768-bit
-// recombinations, their spills and the larger code give back what the multiplier saves -- Miller loop 273.3 -> 269.7..271.7
-// ms, final exponentiation 260.5 -> 262.4..266.7 ms, pairing 521.5..523.3 -> 517.3..519.9 ms (-0.6 %) -- so the shipped
-// build keeps the reduced forms (0); the lazy forms stay as a tested build variant.
+// MACs, bit-identical results, GPU suite green with all three).  Measured at 2^20 (profiles/r2l_lazy_reduction.txt): the
+// 768-bit recombinations, their spills and the larger code give back most of what the multiplier saves.  Everywhere (7):
+// Miller loop 273.3 -> 269.7..271.7 ms, final exponentiation 260.5 -> 262.4..266.7 ms; in the Miller unit only (3, what
+// pairing_kernel.cu ships): pairing 520.5 -> 516.4 ms, prepared 4-pair checks -2.7 %.  Default here (every other unit): 0.
 #ifndef ZKP_LAZY
 #define ZKP_LAZY 0
 #endif
