@@ -9,6 +9,8 @@
 //   2 blocks/SM 310.9;  4 blocks/SM: Fp6-level 266.0 (kept), Fp2-level 266.4;  5 blocks 271.6;  6 blocks 279.5
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #define ZKP_CONVERGED 1
 #define zkp zkp_fe
 #ifndef ZKP_FE_SYNC
@@ -100,23 +102,37 @@ k_fe_stage(int stage, FeScratch fs, uint64_t *__restrict__ out, uint8_t *__restr
 // The six (batched inversion, stage) launch pairs over the state k_pairing parked in `scratch`.
 // `aux` = the helper stream and the fork/join events of the two-stream split (owned by the context, created
 // once in zkp_ctx_create; NULL members = run as one piece).
+// where the batch splits into its two halves (n = no split)
+size_t zkp_fe_split_point(size_t n, const ZkpFeAux *aux) {
+    if (n >= ZKP_FE_SPLIT_MIN && aux && aux->s2 && aux->fork && aux->join) return ((n / 2) + 63) & ~(size_t)63;
+    return n;
+}
+
+// `forked` = the caller has already made aux->s2 wait for `st` (the Miller kernels of the two halves ran on the two streams)
 cudaError_t zkp_launch_fe_stages(void *scratch, size_t n, uint64_t *out, uint8_t *is_one, cudaStream_t st, const ZkpFeAux *aux,
-                                 int *launches) {
+                                 int *launches, int forked) {
     FeScratch fs;
     fs.lanes = (Fp *)scratch;
     fs.norm = fs.lanes + 2 * n * ZKP_FE_LANE_FP;
     fs.n2 = 2 * n;
     dim3 b(ZKP_TPB);
+#ifdef ZKP_FE_CARVEOUT
+    {   // experiment: an explicit L1 / shared-memory split for the stage kernels (percent of shared memory; per device)
+        static std::atomic<unsigned long long> done{0};
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (!((done.load() >> (cur & 63)) & 1ull)) {
+            cudaFuncSetAttribute(k_fe_stage, cudaFuncAttributePreferredSharedMemoryCarveout, ZKP_FE_CARVEOUT);
+            done.fetch_or(1ull << (cur & 63));
+        }
+    }
+#endif
     // The batch runs as two halves on two streams: while one half is in its (latency-bound) batched
     // inversion or in the tail of a stage kernel, the other half's stage kernel keeps the SMs busy.
-    size_t na = n, nb = 0;
-    if (n >= ZKP_FE_SPLIT_MIN && aux && aux->s2 && aux->fork && aux->join) {
-        na = ((n / 2) + 63) & ~(size_t)63;
-        nb = n - na;
-    }
+    size_t na = zkp_fe_split_point(n, aux), nb = n - na;
     *launches = 0;
     cudaStream_t s2 = nb ? aux->s2 : nullptr;
-    if (nb) {
+    if (nb && !forked) {
         cudaError_t e = cudaEventRecord(aux->fork, st);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(s2, aux->fork, 0);
         if (e != cudaSuccess) return e;

@@ -35,10 +35,14 @@
 
 // fe_kernel.cu
 cudaError_t zkp_launch_fe_stages(void *scratch, size_t n, uint64_t *out, uint8_t *is_one, cudaStream_t st, const ZkpFeAux *aux,
-                                 int *launches);
+                                 int *launches, int forked);
+size_t zkp_fe_split_point(size_t n, const ZkpFeAux *aux);
 
 #ifndef ZKP_TPB
 #define ZKP_TPB 128           // threads per block
+#endif
+#ifndef ZKP_MILLER_SPLIT
+#define ZKP_MILLER_SPLIT 0    // 1: the two-stream halves of the final exponentiation start at the Miller kernel (see zkp_launch_k_pairing)
 #endif
 #ifndef ZKP_MIN_BLOCKS
 #define ZKP_MIN_BLOCKS 4      // resident blocks per SM the register allocator must allow (Miller kernel)
@@ -71,8 +75,9 @@ __global__ void __launch_bounds__(ZKP_TPB, ZKP_MIN_BLOCKS)
 k_pairing(int mode, const uint64_t *__restrict__ g1, const uint8_t *__restrict__ g1inf,
           const uint64_t *__restrict__ g2, const uint8_t *__restrict__ g2inf, int k,
           const uint64_t *__restrict__ in12, uint64_t *__restrict__ out, uint8_t *__restrict__ is_one,
-          uint32_t *err, size_t n, FeScratch fs, const Fp *__restrict__ tab, const uint8_t *__restrict__ tabinf, int kf) {
-    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+          uint32_t *err, size_t i0, size_t n, FeScratch fs, const Fp *__restrict__ tab, const uint8_t *__restrict__ tabinf, int kf) {
+    // this launch covers the checks [i0, n) of the batch
+    size_t i = i0 + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1);
     bool live = i < n;
     if (!live) i = n - 1;   // stay converged: redo the last element, store nothing
     size_t e = i * (size_t)k, e2 = i * (size_t)(k - kf);   // the last kf pairs of a check use prepared G2 tables
@@ -123,7 +128,7 @@ cudaError_t zkp_launch_k_pairing(int mode, const uint64_t *g1, const uint8_t *g1
     fs.lanes = (Fp *)scratch;
     fs.norm = fs.lanes ? fs.lanes + 2 * n * ZKP_FE_LANE_FP : nullptr;
     fs.n2 = 2 * n;
-    dim3 g((unsigned)((2 * n + ZKP_TPB - 1) / ZKP_TPB)), b(ZKP_TPB);
+    dim3 b(ZKP_TPB);
 #if ZKP_SMEM_STATE
     // function attributes are per DEVICE: opt in to > 48 KB of dynamic shared memory once on each device that launches
     static std::atomic<unsigned long long> attr_done{0};
@@ -145,16 +150,36 @@ cudaError_t zkp_launch_k_pairing(int mode, const uint64_t *g1, const uint8_t *g1
 #else
 #define ZKP_SM(K) 0
 #endif
-    switch (pair_capacity(k)) {
-        case 1: k_pairing<1><<<g, b, ZKP_SM(1), st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
-        case 2: k_pairing<2><<<g, b, ZKP_SM(2), st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
-        case 4: k_pairing<4><<<g, b, ZKP_SM(4), st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
-        default: k_pairing<8><<<g, b, ZKP_SM(8), st>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, n, fs, (const Fp *)tab, tabinf, kf); break;
+    // ZKP_MILLER_SPLIT: a batch whose final exponentiation runs as two halves on two streams (fe_kernel.cu) splits already HERE,
+    // so that the tail of the first half's Miller kernel is covered by the second half's blocks and the second half's tail by the
+    // first stage kernels of the first half.
+    size_t na = n;
+    int forked = 0;
+#if ZKP_MILLER_SPLIT
+    if (mode & ZKP_DO_FINAL_EXP) na = zkp_fe_split_point(n, aux);
+    if (na < n) {
+        cudaError_t e = cudaEventRecord(aux->fork, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(aux->s2, aux->fork, 0);
+        if (e != cudaSuccess) return e;
+        forked = 1;
     }
-    *launches = 1;
+#endif
+    *launches = 0;
+    for (int half = 0; half < (na < n ? 2 : 1); half++) {
+        size_t lo = half ? na : 0, hi = half ? n : na;
+        cudaStream_t sh = half ? aux->s2 : st;
+        dim3 g((unsigned)((2 * (hi - lo) + ZKP_TPB - 1) / ZKP_TPB));
+        switch (pair_capacity(k)) {
+            case 1: k_pairing<1><<<g, b, ZKP_SM(1), sh>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, lo, hi, fs, (const Fp *)tab, tabinf, kf); break;
+            case 2: k_pairing<2><<<g, b, ZKP_SM(2), sh>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, lo, hi, fs, (const Fp *)tab, tabinf, kf); break;
+            case 4: k_pairing<4><<<g, b, ZKP_SM(4), sh>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, lo, hi, fs, (const Fp *)tab, tabinf, kf); break;
+            default: k_pairing<8><<<g, b, ZKP_SM(8), sh>>>(mode, g1, g1inf, g2, g2inf, k, in12, out, is_one, err, lo, hi, fs, (const Fp *)tab, tabinf, kf); break;
+        }
+        *launches += 1;
+    }
     if (mode & ZKP_DO_FINAL_EXP) {
         int nl = 0;
-        cudaError_t rc = zkp_launch_fe_stages(scratch, n, out, is_one, st, aux, &nl);
+        cudaError_t rc = zkp_launch_fe_stages(scratch, n, out, is_one, st, aux, &nl, forked);
         *launches += nl;
         if (rc != cudaSuccess) return rc;
     }

@@ -171,6 +171,9 @@ ZKP_HD bool fp2_is_zero(const Fp2 &a) { return lane_and(fp_is_zero(a.c)); }
 #ifndef ZKP_LIN
 #define ZKP_LIN ZKP_HD
 #endif
+#ifndef ZKP_SQR_SEL
+#define ZKP_SQR_SEL 0   // 1: fp2_sqr forms a0 by a select on the exchanged value instead of a broadcast shuffle (12 SEL for 12 SHFL)
+#endif
 ZKP_LIN Fp2 fp2_add(Fp2 a, Fp2 b) { Fp2 r; r.c = fp_add(a.c, b.c); return r; }   // src/fp2.rs:216-218
 ZKP_LIN Fp2 fp2_sub(Fp2 a, Fp2 b) { Fp2 r; r.c = fp_sub(a.c, b.c); return r; }   // src/fp2.rs:221-223
 ZKP_LIN Fp2 fp2_neg(Fp2 a) { Fp2 r; r.c = fp_neg(a.c); return r; }               // src/fp2.rs:226-228
@@ -206,7 +209,11 @@ ZKP_NOINLINE Fp2 fp2_sqr(Fp2 a) {
     ZKP_CODE_SYNC(5);
     bool odd = lane_par() != 0;
     Fp pa = fp_xchg(a.c);
+#if ZKP_SQR_SEL
+    Fp x = fp_add_lazy(fp_select(odd, pa, a.c), pa);   // a0 in both lanes without a second shuffle
+#else
     Fp x = fp_add_lazy(fp_bcast<0>(a.c), pa);
+#endif
     Fp y = fp_select(odd, a.c, fp_sub(a.c, pa));
     Fp2 r;
     ZKP_PIPE_ACQUIRE();
