@@ -9,7 +9,8 @@
  *       bls12381_sys_bigint(result:&mut[u32;12], op:u32 /0=mul,1=add/, lhs:&[u32;12], rhs:&[u32;12])   src/fp.rs:376,443
  *       syscall_bls12381_fp_mulmod(lhs:*mut u32, rhs:*const u32)                                       src/fp.rs:126
  *     -> zkp_fp_mul_batch / zkp_tower_op_batch (same canonical 12xu32 = 6xu64 little-endian limbs,
- *        but batched so one call amortises the launch);
+ *        but batched so one call amortises the launch); zkp_sys_bigint / zkp_syscall_fp_mulmod keep the
+ *        precompiles' one-operation shape for code that is not batched yet;
  *   - the tower methods on the path (Fp/Fp2/Fp6/Fp12 mul, square, invert, frobenius_map, conjugate,
  *     mul_by_1 / mul_by_01 / mul_by_014: src/fp2.rs:147-313, src/fp6.rs:102-309, src/fp12.rs:99-210)
  *     -> zkp_tower_op_batch with the ZKP_OP_* code of the method;
@@ -128,6 +129,17 @@ int32_t zkp_fp_mul_batch(zkp_ctx *ctx, const uint64_t *a, const uint64_t *b, uin
 int32_t zkp_fp12_mul_batch(zkp_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
 int32_t zkp_fp12_mul_by_014_batch(zkp_ctx *ctx, const uint64_t *f, const uint64_t *c0_c1_c4,
                                   uint64_t *out, size_t n);
+
+/* Scalar drop-ins with the argument meaning of the reference's zkVM precompile FFI (sp1_zkvm::syscalls, called at
+ * src/fp.rs:126, :376, :443): ONE Fp operation on twelve little-endian u32 limbs (= the transmuted [u64; 6] of
+ * src/fp.rs:124-128), canonical in and out.  zkp_sys_bigint: op 0 = lhs * rhs mod p (src/fp.rs:443), op 1 = lhs + rhs
+ * mod p (src/fp.rs:376), written to `result` (which may alias an operand).  zkp_syscall_fp_mulmod: lhs <- lhs * rhs
+ * mod p in place (src/fp.rs:126).  ctx = NULL uses a process-wide context on device 0, created on first use (the
+ * precompiles carry no handle); unlike the precompiles they return a status (limbs >= p: ZKP_ERR_NONCANONICAL).
+ * One launch per call: they exist so that the crate's `cfg(target_os = "zkvm")` bodies link unchanged; anything
+ * hot belongs on the batch entry points. */
+int32_t zkp_sys_bigint(zkp_ctx *ctx, uint32_t *result, uint32_t op, const uint32_t *lhs, const uint32_t *rhs);
+int32_t zkp_syscall_fp_mulmod(zkp_ctx *ctx, uint32_t *lhs, const uint32_t *rhs);
 
 /* ---- pairing path (host buffers) ---------------------------------------------------------- */
 

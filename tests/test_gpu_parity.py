@@ -589,6 +589,35 @@ def test_config5_sharded_2p24_with_product_gather(engine, coracle):
         multi.close()
 
 
+def test_precompile_shaped_scalar_calls(engine, pyref):
+    """zkp_sys_bigint / zkp_syscall_fp_mulmod: the argument meaning of the reference's zkVM precompile FFI
+    (src/fp.rs:126,376,443) -- twelve little-endian u32 limbs, op 0 = mul, 1 = add, canonical in and out --
+    on the engine's context and on the process-wide one (ctx = NULL), aliasing allowed, limbs >= p rejected."""
+    import random
+    import zkvm_pairings_b200 as z
+    rng = random.Random(0xB16)
+    to32 = lambda v: np.array([(v >> (32 * i)) & 0xFFFFFFFF for i in range(12)], dtype=np.uint32)
+    from32 = lambda a: sum(int(x) << (32 * i) for i, x in enumerate(a))
+    P = pyref.P
+    cases = [(0, 0), (1, P - 1), (P - 1, P - 1), (P - 1, 1), (2, (P + 1) // 2)] + [(rng.randrange(P), rng.randrange(P)) for _ in range(6)]
+    for k, (a, b) in enumerate(cases):
+        dflt = bool(k & 1)
+        assert from32(engine.sys_bigint(0, to32(a), to32(b), use_default_ctx=dflt)) == a * b % P
+        assert from32(engine.sys_bigint(1, to32(a), to32(b), use_default_ctx=dflt)) == (a + b) % P
+        lhs = to32(a)
+        engine.syscall_fp_mulmod(lhs, to32(b), use_default_ctx=dflt)
+        assert from32(lhs) == a * b % P
+    # `result` may alias an operand (the crate's mul_assign passes lhs as the output, src/fp.rs:118-130)
+    lib, x = engine._lib, to32(cases[-1][0])
+    assert lib.zkp_sys_bigint(None, x.ctypes.data, 1, x.ctypes.data, x.ctypes.data) == 0
+    assert from32(x) == 2 * cases[-1][0] % P
+    with pytest.raises(z.ZkpError) as ei:
+        engine.sys_bigint(0, to32(P), to32(1))
+    assert ei.value.code == -3
+    with pytest.raises(z.ZkpError):
+        engine.sys_bigint(2, to32(1), to32(1))
+
+
 def test_imad_peak_probe(engine):
     wide = engine.imad_peak(0)
     lo = engine.imad_peak(1)

@@ -50,6 +50,22 @@ def test_no_cuda_device_fails_loudly(lib):
     assert ei.value.code == -4
 
 
+def test_precompile_shaped_calls_have_no_cpu_path(lib):
+    """zkp_sys_bigint / zkp_syscall_fp_mulmod (the reference's zkVM precompile FFI, src/fp.rs:126,376,443): argument
+    checks happen on the host; without a GPU the process-wide context cannot be created and the call fails with
+    ZKP_ERR_NO_DEVICE -- it never computes on the CPU."""
+    import zkvm_pairings_b200 as z
+    a = np.arange(1, 13, dtype=np.uint32)
+    out = np.zeros(12, dtype=np.uint32)
+    assert lib.zkp_sys_bigint(None, None, 0, _p(a), _p(a)) == -1
+    assert lib.zkp_sys_bigint(None, _p(out), 7, _p(a), _p(a)) == -1 and b"op" in lib.zkp_last_error()
+    assert lib.zkp_syscall_fp_mulmod(None, None, _p(a)) == -1
+    if z.device_count() == 0:
+        assert lib.zkp_sys_bigint(None, _p(out), 0, _p(a), _p(a)) == -4
+        assert lib.zkp_syscall_fp_mulmod(None, _p(out), _p(a)) == -4
+        assert not out.any()
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "zkvm_pairings_b200")
     for dirpath, _, files in os.walk(pkg):

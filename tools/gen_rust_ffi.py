@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TYPES = [
     (r"^zkp_ctx \*\*$", "*mut *mut ZkpCtx"), (r"^const zkp_ctx \*$", "*const ZkpCtx"), (r"^zkp_ctx \*$", "*mut ZkpCtx"),
     (r"^const uint64_t \*$", "*const u64"), (r"^uint64_t \*$", "*mut u64"), (r"^const uint8_t \*$", "*const u8"),
-    (r"^uint8_t \*$", "*mut u8"), (r"^uint32_t \*$", "*mut u32"), (r"^const void \*$", "*const c_void"),
+    (r"^uint8_t \*$", "*mut u8"), (r"^const uint32_t \*$", "*const u32"), (r"^uint32_t \*$", "*mut u32"), (r"^uint32_t$", "u32"), (r"^const void \*$", "*const c_void"),
     (r"^void \*$", "*mut c_void"), (r"^const int \*$", "*const c_int"), (r"^double \*$", "*mut f64"),
     (r"^const char \*$", "*const c_char"), (r"^size_t$", "usize"), (r"^int32_t$", "i32"), (r"^uint64_t$", "u64"),
     (r"^int$", "c_int"), (r"^void$", "()"),

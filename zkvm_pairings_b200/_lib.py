@@ -23,6 +23,8 @@ SYMBOLS = {
     "zkp_version": (ctypes.c_char_p, []),
     "zkp_tower_op_batch": (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_int32, c_u64p, c_u64p, c_u64p, c_u8p, ctypes.c_size_t]),
     "zkp_fp_mul_batch": (ctypes.c_int32, [ctypes.c_void_p, c_u64p, c_u64p, c_u64p, ctypes.c_size_t]),
+    "zkp_sys_bigint": (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]),
+    "zkp_syscall_fp_mulmod": (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "zkp_fp12_mul_batch": (ctypes.c_int32, [ctypes.c_void_p, c_u64p, c_u64p, c_u64p, ctypes.c_size_t]),
     "zkp_fp12_mul_by_014_batch": (ctypes.c_int32, [ctypes.c_void_p, c_u64p, c_u64p, c_u64p, ctypes.c_size_t]),
     "zkp_miller_loop_batch": (ctypes.c_int32, [ctypes.c_void_p, c_u64p, c_u8p, c_u64p, c_u8p, ctypes.c_size_t, c_u64p]),

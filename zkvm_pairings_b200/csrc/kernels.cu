@@ -885,6 +885,37 @@ int32_t zkp_tower_op_batch(zkp_ctx *ctx, int32_t op, const uint64_t *a, const ui
 int32_t zkp_fp_mul_batch(zkp_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
     return zkp_tower_op_batch(ctx, OP_FP_MUL, a, b, out, nullptr, n);
 }
+// The reference's zkVM precompile FFI, one Fp operation per call (src/fp.rs:126,376,443).  The precompiles carry no
+// handle: ctx = NULL selects a process-wide context on device 0 created on first use (never destroyed).
+static zkp_ctx *default_ctx(int32_t &rc) {
+    static std::mutex mu;
+    static zkp_ctx *ctx = nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    rc = ZKP_OK;
+    if (!ctx) {
+        int dev0 = 0;
+        rc = zkp_ctx_create(&dev0, 1, &ctx);
+        if (rc != ZKP_OK) ctx = nullptr;
+    }
+    return ctx;
+}
+int32_t zkp_sys_bigint(zkp_ctx *ctx, uint32_t *result, uint32_t op, const uint32_t *lhs, const uint32_t *rhs) {
+    if (!result || !lhs || !rhs) return fail(ZKP_ERR_INVALID_ARG, "NULL limb pointer");
+    if (op > 1) return fail(ZKP_ERR_INVALID_ARG, "op must be 0 (mul) or 1 (add)");
+    if (!ctx) {
+        int32_t rc;
+        ctx = default_ctx(rc);
+        if (!ctx) return rc;
+    }
+    // twelve u32 limbs = the little-endian [u64; 6] of src/fp.rs:24 (the crate transmutes, src/fp.rs:124-128)
+    uint64_t a[6], b[6], o[6];
+    memcpy(a, lhs, sizeof a);
+    memcpy(b, rhs, sizeof b);
+    int32_t rc = zkp_tower_op_batch(ctx, op == 0 ? OP_FP_MUL : OP_FP_ADD, a, b, o, nullptr, 1);
+    if (rc == ZKP_OK) memcpy(result, o, sizeof o);
+    return rc;
+}
+int32_t zkp_syscall_fp_mulmod(zkp_ctx *ctx, uint32_t *lhs, const uint32_t *rhs) { return zkp_sys_bigint(ctx, lhs, 0, lhs, rhs); }
 int32_t zkp_fp12_mul_batch(zkp_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
     return zkp_tower_op_batch(ctx, OP_FP12_MUL, a, b, out, nullptr, n);
 }

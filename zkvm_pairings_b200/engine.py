@@ -151,6 +151,23 @@ class PairingEngine:
         self._check(self._lib.zkp_fp_mul_batch(self._ctx, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
         return out
 
+    def sys_bigint(self, op: int, lhs, rhs, use_default_ctx: bool = False):
+        """The reference's zkVM precompile `bls12381_sys_bigint` (src/fp.rs:376,443): ONE Fp operation on twelve
+        little-endian u32 limbs, op 0 = mul, 1 = add.  use_default_ctx passes ctx = NULL (the process-wide context)."""
+        lhs = np.ascontiguousarray(lhs, dtype=np.uint32).reshape(12)
+        rhs = np.ascontiguousarray(rhs, dtype=np.uint32).reshape(12)
+        out = np.zeros(12, dtype=np.uint32)
+        self._check(self._lib.zkp_sys_bigint(None if use_default_ctx else self._ctx, _ptr(out), op, _ptr(lhs), _ptr(rhs)))
+        return out
+
+    def syscall_fp_mulmod(self, lhs, rhs, use_default_ctx: bool = False):
+        """`syscall_bls12381_fp_mulmod` (src/fp.rs:126): lhs <- lhs * rhs mod p IN PLACE (lhs must be a uint32[12] array)."""
+        if not (isinstance(lhs, np.ndarray) and lhs.dtype == np.uint32 and lhs.size == 12 and lhs.flags["C_CONTIGUOUS"]):
+            raise ValueError("lhs must be a contiguous uint32[12] array (updated in place)")
+        rhs = np.ascontiguousarray(rhs, dtype=np.uint32).reshape(12)
+        self._check(self._lib.zkp_syscall_fp_mulmod(None if use_default_ctx else self._ctx, _ptr(lhs), _ptr(rhs)))
+        return lhs
+
     def fp12_mul_batch(self, a, b):
         a, b = _np64(a, 72), _np64(b, 72)
         out = np.empty_like(a)
