@@ -13,9 +13,13 @@
 // where it used to lose to instruction-fetch stalls.  Miller loop only, 2^20 (profiles/r1o_occupancy_variants.txt):
 //   2 blocks/SM (244 registers): no points 311.7 ms, once per iteration 305.6, Fp6-level 310.4
 //   3 blocks/SM (168): once per iteration 287.5, Fp6-level 289.1
-//   4 blocks/SM (128): once per iteration 287.1, Fp6-level 280.2 (kept), Fp2-level 286.3;  5 blocks 307.5, 6 blocks 315.9
+//   4 blocks/SM (128): once per iteration 287.1, Fp6-level 280.2, Fp2-level 286.3;  5 blocks 307.5, 6 blocks 315.9
+// With the lazy forms below (hot code ~100 KB) a rendezvous at every Fp2-level body (5) measures slightly better in steady state --
+// three interleaved repetitions at 2^20 (profiles/r2z_sync_order_variants.txt): pairing 518.3..518.4 -> 517.3..517.5 ms, together with
+// ZKP_LAZY_ORDER 516.6..516.8 ms (-0.3 %); Miller loop alone 272.9..274.8 -> 270.5..270.7 ms; no difference at 2^16.  The counters of a
+// single cold launch under ncu do not show why (instruction-fetch stalls 0.43 -> 0.50 per issue, profiles/r2aa_ncu_summary.txt).
 #ifndef ZKP_MILLER_SYNC
-#define ZKP_MILLER_SYNC 4
+#define ZKP_MILLER_SYNC 5
 #endif
 #define ZKP_LOOP_SYNC ZKP_MILLER_SYNC
 // Lazy reduction (tower.cuh ZKP_LAZY, fp.cuh FpW) in THIS unit only: ZKP_MILLER_LAZY = 3 (shipped) recombines UNREDUCED Fp2

@@ -231,6 +231,9 @@ ZKP_NOINLINE Fp2 fp2_sqr(Fp2 a) {
 #ifndef ZKP_LAZY
 #define ZKP_LAZY 0
 #endif
+#ifndef ZKP_LAZY_ORDER
+#define ZKP_LAZY_ORDER 1   // order of the sums in the lazy fp6_mul (below); 1 = fewer unreduced values alive across the last calls
+#endif
 ZKP_NOINLINE FpW fp2_mulw(Fp2 a, Fp2 b) {
     ZKP_CODE_SYNC(5);
     bool odd = lane_par() != 0;
@@ -320,6 +323,28 @@ ZKP_HD void fp6_mul_nr(Fp6 &r, const Fp6 &a) {
 //   c1 = w1 + xi v2 - v0 - v1:    xi v2: even [-8, 8], odd [0, 16];                           c1 in [-24, 24]  -> + 24: [0, 48]
 //   c2 = w2 + v1 - v0 - v2:                                                                   c2 in [-16, 16]  -> + 16: [0, 32]
 // all below 2^768 = 96.9 p^2 and below 68 p^2 (results < 8p: two correction steps).
+#if ZKP_LAZY_ORDER
+// same sums in an order that keeps fewer unreduced values alive across the last product and reduction calls (after c0 only
+// d1 = xi v2 - v0 - v1 and d2 = v1 - v0 - v2 instead of v0, v1, v2; arithmetic modulo 2^768, so the reduced values are the
+// same): neutral by itself, -0.1 % on top of the finer rendezvous points (profiles/r2z_sync_order_variants.txt) -- shipped
+ZKP_NOINLINE void fp6_mul(Fp6 &r, const Fp6 &a, const Fp6 &b) {
+    ZKP_CODE_SYNC(4);
+    FpW w = fp2_mulw(fp2_add(a.c1, a.c2), fp2_add(b.c1, b.c2));
+    FpW v1 = fp2_mulw(a.c1, b.c1);
+    FpW v2 = fp2_mulw(a.c2, b.c2);
+    FpW t0 = fpw_mul_nr(fpw_sub(fpw_add(v1, v2), w));
+    FpW v0 = fp2_mulw(a.c0, b.c0);
+    Fp2 c0 = fp2_redc<1>(fpw_add_const(fpw_sub(v0, t0), ZKP_P2X32));
+    FpW d1 = fpw_sub(fpw_mul_nr(v2), fpw_add(v0, v1));
+    FpW d2 = fpw_sub(v1, fpw_add(v0, v2));
+    w = fp2_mulw(fp2_add(a.c0, a.c1), fp2_add(b.c0, b.c1));
+    Fp2 c1 = fp2_redc<1>(fpw_add_const(fpw_add(w, d1), ZKP_P2X24));
+    w = fp2_mulw(fp2_add(a.c0, a.c2), fp2_add(b.c0, b.c2));
+    r.c2 = fp2_redc<1>(fpw_add_const(fpw_add(w, d2), ZKP_P2X16));
+    r.c0 = c0;
+    r.c1 = c1;
+}
+#else
 ZKP_NOINLINE void fp6_mul(Fp6 &r, const Fp6 &a, const Fp6 &b) {
     ZKP_CODE_SYNC(4);
     FpW v1 = fp2_mulw(a.c1, b.c1);
@@ -337,6 +362,7 @@ ZKP_NOINLINE void fp6_mul(Fp6 &r, const Fp6 &a, const Fp6 &b) {
     r.c0 = c0;
     r.c1 = c1;
 }
+#endif
 #else
 ZKP_NOINLINE void fp6_mul(Fp6 &r, const Fp6 &a, const Fp6 &b) {
     ZKP_CODE_SYNC(4);
