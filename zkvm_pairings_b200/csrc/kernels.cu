@@ -335,17 +335,17 @@ static cudaError_t launch_pairing(zkp_ctx *ctx, DevState &d, int mode, const uin
                                   uint64_t *out, uint8_t *is_one, uint32_t *err, cudaStream_t st,
                                   const void *tab = nullptr, const uint8_t *tabinf = nullptr, int kf = 0) {
     if (n == 0) return cudaSuccess;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (ctx->timing) {
-        cudaEventCreate(&e0);
-        cudaEventCreate(&e1);
-        cudaEventRecord(e0, st);
-    }
     // the final exponentiation parks its state between launches in stream-ordered scratch memory
     void *scratch = nullptr;
     if (mode & 2) {
         cudaError_t e = cudaMallocFromPoolAsync(&scratch, zkp_fe_scratch_bytes(n), d.pool, st);
         if (e != cudaSuccess) return e;
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->timing) {   // (created after the only early return, so that no event is left behind)
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
     }
     int nl = 0;
     const ZkpFeAux *aux = &d.fe_aux[st == d.stream[0] ? 0 : st == d.stream[1] ? 1 : 2];
@@ -1182,28 +1182,32 @@ int32_t zkp_imad_peak(zkp_ctx *ctx, int32_t dev, int32_t kind, double *macs_per_
     const int iters = 1 << 13;
     const double per_thread = (double)iters * (kind == 2 ? 12.0 : 8.0);
     static const int geom[][2] = {{8, 256}, {4, 256}, {16, 128}, {8, 128}, {4, 512}};   // blocks per SM, threads per block
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
+    struct EventPair {   // destroyed on every exit path
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~EventPair() {
+            if (a) cudaEventDestroy(a);
+            if (b) cudaEventDestroy(b);
+        }
+    } ev;
+    CU(cudaEventCreate(&ev.a));
+    CU(cudaEventCreate(&ev.b));
     double best_rate = 0;
     for (const auto &g : geom) {
         const int blocks = d.sms * g[0], threads = g[1];
         for (int rep = 0; rep < 3; rep++) {
-            CU(cudaEventRecord(e0, st));
+            CU(cudaEventRecord(ev.a, st));
             if (kind == 0) k_imad_peak<0><<<blocks, threads, 0, st>>>(sink + 0, iters);
             else if (kind == 1) k_imad_peak<1><<<blocks, threads, 0, st>>>(sink + 0, iters);
             else k_imad_peak<2><<<blocks, threads, 0, st>>>(sink + 0, iters);
             ctx->launches++;
-            CU(cudaEventRecord(e1, st));
-            CU(cudaEventSynchronize(e1));
+            CU(cudaEventRecord(ev.b, st));
+            CU(cudaEventSynchronize(ev.b));
             float ms = 0;
-            CU(cudaEventElapsedTime(&ms, e0, e1));
+            CU(cudaEventElapsedTime(&ms, ev.a, ev.b));
             double rate = per_thread * blocks * threads / (ms * 1e-3);
             if (rep > 0 && rate > best_rate) best_rate = rate;
         }
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     CU(cudaMemsetAsync(d.d_err, 0, sizeof(uint32_t), st));
     CU(cudaStreamSynchronize(st));
     *macs_per_second = best_rate;
